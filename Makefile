@@ -1,0 +1,33 @@
+# Top-level build: product library (CUDA, sm_100a), data generator, CPU checker.
+NVCC   ?= /usr/local/cuda/bin/nvcc
+CC     ?= gcc
+CXX    ?= g++
+PKG    := streamly_lz4_b200
+CSRC   := $(PKG)/csrc
+ARCH   := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v -Iinclude -I$(CSRC)
+
+LIB    := $(PKG)/libb200lz4.so
+GEN    := $(PKG)/datagen/libb200gen.so
+HOSTT  := $(PKG)/csrc/host_mirror_test
+
+CU_SRCS  := $(wildcard $(CSRC)/*.cu)
+CU_HDRS  := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.hpp) include/b200lz4.h
+
+all: $(LIB) $(GEN) oracle
+
+$(LIB): $(CU_SRCS) $(CU_HDRS)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRCS) 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
+	@grep -E "registers|spill|error|warning" $(CSRC)/ptxas.log | sort | uniq -c | sort -rn | head -40 || true
+
+$(GEN): $(PKG)/datagen/datagen.c
+	$(CC) -O2 -fPIC -shared -o $@ $<
+
+oracle:
+	$(MAKE) -s -C oracle
+
+clean:
+	rm -f $(LIB) $(GEN) $(CSRC)/ptxas.log
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean
