@@ -1,0 +1,363 @@
+"""Host-side mirror of the reference's public API over the C ABI.
+
+Names, argument meaning and error behaviour follow `Streamly.LZ4`
+(src/Streamly/LZ4.hs:40-122) and `Streamly.Internal.LZ4`
+(src/Streamly/Internal/LZ4.hs:342-567):
+
+    compress_chunks(cfg, speed, chunks)      compressChunks   LZ4.hs:94-100   / Internal/LZ4.hs:353-394
+    decompress_chunks(cfg, chunks)           decompressChunks LZ4.hs:114-122  (= resize then raw decode)
+    decompress_chunks_raw(cfg, chunks)       decompressChunksRawD  Internal/LZ4.hs:539-567
+    resize_chunks(cfg, frame_cfg, chunks)    resizeChunksD    Internal/LZ4.hs:432-523
+    BlockConfig / BlockSize / FrameConfig    Internal/LZ4/Config.hs:41-161
+
+A "stream" is any Python iterable of bytes-like arrays.  Where the reference
+calls the codec once per array, this mirror gathers arrays into a pinned host
+batch and makes ONE call into libb200lz4.so per batch (the behaviour the
+patched Haskell shim in INTEGRATION.md has); results are yielded in order, one
+output array per input array, with the reference's block header layout.
+
+All codec work happens in the CUDA library; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+from dataclasses import dataclass, replace
+from typing import Iterable, Iterator, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+LZ4_MAX_INPUT_SIZE = 0x7E000000
+
+
+class BlockSize(enum.Enum):                 # Config.hs:104-119
+    BlockHasSize = 0
+    BlockMax64KB = 64 * 1024
+    BlockMax256KB = 256 * 1024
+    BlockMax1MB = 1024 * 1024
+    BlockMax4MB = 4 * 1024 * 1024
+
+
+@dataclass(frozen=True)
+class BlockConfig:                           # Config.hs:121-134
+    block_size: BlockSize = BlockSize.BlockHasSize
+    independent: bool = False                # setBlockIndependence (a stub in the reference, Config.hs:142-146)
+
+    @property
+    def meta_size(self) -> int:              # metaSize, Internal/LZ4.hs:177-181
+        return 8 if self.block_size is BlockSize.BlockHasSize else 4
+
+    @property
+    def max_block_size(self) -> int:         # Internal/LZ4.hs:275-281
+        return LZ4_MAX_INPUT_SIZE if self.block_size is BlockSize.BlockHasSize else self.block_size.value
+
+
+@dataclass(frozen=True)
+class FrameConfig:                           # Config.hs:41-48
+    has_end_mark: bool = False
+
+
+default_block_config = BlockConfig()
+default_frame_config = FrameConfig()
+
+
+def set_block_max_size(bs: BlockSize):       # setBlockMaxSize, Config.hs:136-140
+    return lambda cfg: replace(cfg, block_size=bs)
+
+
+def set_block_independence(flag: bool):      # setBlockIndependence, Config.hs:142-146 (implemented here)
+    return lambda cfg: replace(cfg, independent=flag)
+
+
+def set_frame_end_mark(flag: bool):          # setFrameEndMark, Config.hs:60-63
+    return lambda cfg: replace(cfg, has_end_mark=flag)
+
+
+class LZ4Error(RuntimeError):
+    pass
+
+
+class Context:
+    """One b200lz4_ctx (device + CUDA stream + staging arenas) with pinned batch buffers."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.b200lz4_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise LZ4Error(f"b200lz4_ctx_create({device}) failed ({rc}): {_lib.last_error()}")
+        self.handle = h
+        self.device = device
+        self._pins = {}
+
+    def close(self):
+        if self.handle:
+            for p, _ in self._pins.values():
+                self.lib.b200lz4_host_free(p)
+            self._pins = {}
+            self.lib.b200lz4_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pinned(self, name: str, nbytes: int) -> np.ndarray:
+        """A reusable page-locked uint8 buffer of at least nbytes."""
+        cur = self._pins.get(name)
+        if cur is None or cur[1].size < nbytes:
+            if cur is not None:
+                self.lib.b200lz4_host_free(cur[0])
+            cap = max(int(nbytes * 1.25) + 4096, 1 << 16)
+            p = self.lib.b200lz4_host_alloc(cap)
+            if not p:
+                raise LZ4Error("b200lz4_host_alloc failed: " + _lib.last_error())
+            arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(cap,))
+            self._pins[name] = cur = (p, arr)
+        return cur[1]
+
+    def timing(self):
+        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        self.lib.b200lz4_last_timing(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return {"h2d_ms": a.value, "kernel_ms": b.value, "d2h_ms": c.value}
+
+    def launch_count(self) -> int:
+        return int(self.lib.b200lz4_launch_count(self.handle))
+
+    # ---- raw batch calls on numpy buffers --------------------------------
+    def compress_batch(self, src: np.ndarray, src_off: np.ndarray, src_len: np.ndarray,
+                       accel: int, header: int, dst: np.ndarray,
+                       stream_first: Optional[np.ndarray] = None, streams: Optional[Sequence] = None):
+        n = len(src_len)
+        dst_off = np.zeros(n + 1, dtype=np.int64)
+        out_len = np.zeros(n, dtype=np.int32)
+        sf = None if stream_first is None else np.ascontiguousarray(stream_first, dtype=np.int32)
+        ns = 0 if sf is None else len(sf) - 1
+        sh = None
+        if streams is not None:
+            sh = (ctypes.c_void_p * ns)(*[s.handle for s in streams])
+        rc = self.lib.b200lz4_compress_batch(
+            self.handle, src.ctypes.data, src.size, src_off.ctypes.data, src_len.ctypes.data, n,
+            None if sf is None else sf.ctypes.data, ns, sh, accel, header,
+            dst.ctypes.data, dst.size, dst_off.ctypes.data, out_len.ctypes.data)
+        return rc, dst_off, out_len
+
+    def decompress_batch(self, src: np.ndarray, src_off: np.ndarray, src_len: np.ndarray,
+                         header: int, max_block: int, dst: np.ndarray,
+                         stream_first: Optional[np.ndarray] = None, streams: Optional[Sequence] = None):
+        n = len(src_len)
+        dst_off = np.zeros(n + 1, dtype=np.int64)
+        out_len = np.zeros(n, dtype=np.int32)
+        sf = None if stream_first is None else np.ascontiguousarray(stream_first, dtype=np.int32)
+        ns = 0 if sf is None else len(sf) - 1
+        sh = None
+        if streams is not None:
+            sh = (ctypes.c_void_p * ns)(*[s.handle for s in streams])
+        rc = self.lib.b200lz4_decompress_batch(
+            self.handle, src.ctypes.data, src.size, src_off.ctypes.data, src_len.ctypes.data, n,
+            None if sf is None else sf.ctypes.data, ns, sh, header, max_block,
+            dst.ctypes.data, dst.size, dst_off.ctypes.data, out_len.ctypes.data)
+        return rc, dst_off, out_len
+
+
+class CompressStream:
+    """Device-resident LZ4_stream_t (c_createStream / c_freeStream, Internal/LZ4.hs:105-110)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        h = ctypes.c_void_p()
+        rc = ctx.lib.b200lz4_cstream_create(ctx.handle, ctypes.byref(h))
+        if rc != 0:
+            raise LZ4Error("b200lz4_cstream_create: " + _lib.last_error())
+        self.handle = h
+
+    def peek(self):
+        table = np.zeros(4096, dtype=np.uint32)
+        off = ctypes.c_uint32()
+        rc = self.ctx.lib.b200lz4_cstream_peek(self.handle, table.ctypes.data, ctypes.addressof(off))
+        if rc != 0:
+            raise LZ4Error(_lib.last_error())
+        return table, off.value
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.b200lz4_cstream_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.free()
+        except Exception:
+            pass
+
+
+class DecompressStream:
+    """Device-resident LZ4_streamDecode_t (c_createStreamDecode, Internal/LZ4.hs:113-118)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        h = ctypes.c_void_p()
+        rc = ctx.lib.b200lz4_dstream_create(ctx.handle, ctypes.byref(h))
+        if rc != 0:
+            raise LZ4Error("b200lz4_dstream_create: " + _lib.last_error())
+        self.handle = h
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.b200lz4_dstream_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.free()
+        except Exception:
+            pass
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _batches(chunks: Iterable, batch_arrays: int, batch_bytes: int):
+    group: List[bytes] = []
+    size = 0
+    for c in chunks:
+        b = c if isinstance(c, (bytes, bytearray, memoryview)) else np.ascontiguousarray(c, dtype=np.uint8).tobytes()
+        group.append(b)
+        size += len(b)
+        if len(group) >= batch_arrays or size >= batch_bytes:
+            yield group
+            group, size = [], 0
+    if group:
+        yield group
+
+
+def _gather(ctx: Context, name: str, arrays: Sequence[bytes]):
+    lens = np.array([len(a) for a in arrays], dtype=np.int32)
+    offs = np.zeros(len(arrays), dtype=np.int64)
+    # 16-byte aligned starts; a gap keeps consecutive arrays non-adjacent like separate Haskell arrays
+    strides = (lens.astype(np.int64) + 16 + 15) // 16 * 16
+    if len(arrays) > 1:
+        offs[1:] = np.cumsum(strides[:-1])
+    total = int(strides.sum())
+    buf = ctx.pinned(name, total)
+    for a, o, n in zip(arrays, offs, lens):
+        if n:
+            buf[o:o + n] = np.frombuffer(a, dtype=np.uint8)
+    return buf[:total], offs, lens
+
+
+def compress_chunks(cfg: BlockConfig, speed: int, chunks: Iterable, *, ctx: Optional[Context] = None,
+                    batch_arrays: int = 4096, batch_bytes: int = 256 << 20) -> Iterator[bytes]:
+    """compressChunks cfg speed (LZ4.hs:94-100): each input array becomes one framed LZ4 block.
+
+    Linked mode (default, like the reference): one device stream state for the whole
+    stream, arrays strictly in order.  cfg.independent: fresh state per array.
+    """
+    ctx = ctx or default_context()
+    speed = max(int(speed), 0)                                   # Internal/LZ4.hs:364
+    header = cfg.meta_size
+    stream = None if cfg.independent else CompressStream(ctx)    # CompressInit, Internal/LZ4.hs:367-376
+    try:
+        for group in _batches(chunks, batch_arrays, batch_bytes):
+            for a in group:
+                if len(a) >= 2 * 1024 * 1024 * 1024:             # Internal/LZ4.hs:384-385
+                    raise LZ4Error("compressChunksD: Array element > 2 GB encountered")
+                if len(a) > cfg.max_block_size:                  # Internal/LZ4.hs:237-241
+                    raise LZ4Error(f"compressChunk: Source array length {len(a)} exceeds the maximum block size "
+                                   f"of {cfg.max_block_size}")
+            src, offs, lens = _gather(ctx, "c_src", group)
+            cap = int((lens.astype(np.int64) + lens // 255 + 16 + header).sum())
+            dst = ctx.pinned("c_dst", cap)
+            sf = None if stream is None else np.array([0, len(group)], dtype=np.int32)
+            rc, dst_off, out_len = ctx.compress_batch(src, offs, lens, speed, header, dst, sf,
+                                                      None if stream is None else [stream])
+            if rc != 0:                                          # Internal/LZ4.hs:257-260
+                raise LZ4Error(f"compressChunk: c_compressFastContinue failed ({rc}): {_lib.last_error()}")
+            for i in range(len(group)):
+                yield dst[dst_off[i]:dst_off[i + 1]].tobytes()
+    finally:
+        if stream is not None:
+            stream.free()                                        # CompressDone, Internal/LZ4.hs:393-394
+
+
+def decompress_chunks_raw(cfg: BlockConfig, chunks: Iterable, *, ctx: Optional[Context] = None,
+                          batch_arrays: int = 4096, batch_bytes: int = 256 << 20) -> Iterator[bytes]:
+    """decompressChunksRawD (Internal/LZ4.hs:539-567): every input array is exactly one framed block."""
+    ctx = ctx or default_context()
+    header = cfg.meta_size
+    max_block = 0 if cfg.block_size is BlockSize.BlockHasSize else cfg.block_size.value
+    stream = None if cfg.independent else DecompressStream(ctx)
+    try:
+        for group in _batches(chunks, batch_arrays, batch_bytes // 2):
+            src, offs, lens = _gather(ctx, "d_src", group)
+            if header == 8:
+                caps = [max(int.from_bytes(a[4:8], "little", signed=True), 0) if len(a) >= 8 else 0 for a in group]
+                cap = int(sum(caps))
+            else:
+                cap = (max_block + 16) * len(group)
+            dst = ctx.pinned("d_dst", cap + 64)
+            sf = None if stream is None else np.array([0, len(group)], dtype=np.int32)
+            rc, dst_off, out_len = ctx.decompress_batch(src, offs, lens, header, max_block, dst, sf,
+                                                        None if stream is None else [stream])
+            if rc != 0:                                          # Internal/LZ4.hs:309-330
+                raise LZ4Error(f"decompressChunk: c_decompressSafeContinue failed ({rc}): {_lib.last_error()}")
+            for i in range(len(group)):
+                yield dst[dst_off[i]:dst_off[i] + out_len[i]].tobytes()
+    finally:
+        if stream is not None:
+            stream.free()
+
+
+def resize_chunks(cfg: BlockConfig, frame_cfg: FrameConfig, chunks: Iterable) -> Iterator[bytes]:
+    """resizeChunksD (Internal/LZ4.hs:432-523): re-frame an arbitrarily fragmented compressed
+    stream into one array per [header][block].  The header walk runs in b200lz4_reframe."""
+    lib = _lib.load()
+    header = cfg.meta_size
+    buf = bytearray()
+    max_blocks = 1 << 16
+    off = np.zeros(max_blocks, dtype=np.int64)
+    ln = np.zeros(max_blocks, dtype=np.int32)
+    nf, used, ended = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+
+    def drain():
+        while True:
+            raw = (ctypes.c_char * len(buf)).from_buffer(buf) if buf else None
+            rc = lib.b200lz4_reframe(raw, len(buf), header, int(frame_cfg.has_end_mark),
+                                     off.ctypes.data, ln.ctypes.data, max_blocks,
+                                     ctypes.byref(nf), ctypes.byref(used), ctypes.byref(ended))
+            del raw
+            if rc != 0:
+                raise LZ4Error("resizeChunksD: " + _lib.last_error())
+            out = [bytes(buf[off[k]:off[k] + ln[k]]) for k in range(nf.value)]
+            del buf[:used.value]
+            yield from out
+            if ended.value or nf.value < max_blocks:
+                return
+
+    for c in chunks:
+        buf += bytes(c)
+        yield from drain()
+        if ended.value:
+            return                                               # RFooter -> Stop, Internal/LZ4.hs:506-522
+    if buf:
+        raise LZ4Error("resizeChunksD: Incomplete block")        # RAccumulate + Stop, Internal/LZ4.hs:505
+    if frame_cfg.has_end_mark:
+        raise LZ4Error("resizeChunksD: No end mark found")       # RInit + Stop, Internal/LZ4.hs:493-496
+
+
+def decompress_chunks(cfg: BlockConfig, chunks: Iterable, *, ctx: Optional[Context] = None, **kw) -> Iterator[bytes]:
+    """decompressChunks (LZ4.hs:114-122) = decompressChunksRawD . resizeChunksD."""
+    return decompress_chunks_raw(cfg, resize_chunks(cfg, default_frame_config, chunks), ctx=ctx, **kw)

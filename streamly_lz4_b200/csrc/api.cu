@@ -1,0 +1,684 @@
+// api.cu -- the C ABI of libb200lz4.so (see include/b200lz4.h): contexts, staging,
+// the batched host/device entry points, re-framing and the legacy LZ4_* aliases.
+// There is no CPU codec in this library: every compress/decompress call runs the
+// sm_100a kernels, and fails with B200LZ4_E_CUDA when no such device is usable.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "b200lz4.h"
+#include "kernels.h"
+
+using namespace b200lz4;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int fail_cuda(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return B200LZ4_E_CUDA;
+}
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda(e__, #call); } while (0)
+
+inline int bound_of(int n) { return ((unsigned)n > (unsigned)kMaxInput) ? 0 : n + n / 255 + 16; }
+inline int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(B200LZ4_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(B200LZ4_E_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct b200lz4_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Scratch* scratch = nullptr;
+    DevBuf d_src, d_slots, d_out, d_desc;
+    PinBuf h_desc;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float t_h2d = 0, t_kernel = 0, t_d2h = 0;
+    int64_t launches = 0;
+};
+
+struct b200lz4_cstream {
+    b200lz4_ctx* ctx; CState* d_state; uint8_t* d_dict; uint32_t dict_cap; uint32_t last_len;
+};
+struct b200lz4_dstream {
+    b200lz4_ctx* ctx; DState* d_state;
+};
+
+namespace {
+
+// carve typed arrays out of one host/device descriptor block
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t o = off; off = (off + bytes + 15) & ~size_t(15); return o; }
+};
+
+int check_blocks(const int64_t* off, const int32_t* len, int n, int64_t bytes)
+{
+    for (int i = 0; i < n; i++) {
+        if (len[i] < 0 || off[i] < 0 || off[i] + (int64_t)len[i] > bytes)
+            return fail(B200LZ4_E_ARG, "block " + std::to_string(i) + " lies outside the source buffer");
+    }
+    return 0;
+}
+int check_streams(const int32_t* first, int n_streams, int n_blocks)
+{
+    if (!first) return 0;
+    if (n_streams < 0 || (n_streams == 0 && n_blocks != 0)) return fail(B200LZ4_E_ARG, "n_streams");
+    if (n_streams == 0) return 0;
+    if (first[0] != 0 || first[n_streams] != n_blocks) return fail(B200LZ4_E_ARG, "stream_first must start at 0 and end at n_blocks");
+    for (int s = 0; s < n_streams; s++) if (first[s] > first[s + 1]) return fail(B200LZ4_E_ARG, "stream_first must be non-decreasing");
+    return 0;
+}
+
+int set_dict_fields(CState* d_state, uint8_t* buf, uint32_t cap, cudaStream_t st)
+{
+    struct { uint32_t dict_cap; uint32_t pad; uint8_t* dict_buf; } f{cap, 0, buf};
+    static_assert(offsetof(CState, dict_buf) == offsetof(CState, dict_cap) + 8, "CState layout");
+    CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d_state) + offsetof(CState, dict_cap), &f, sizeof f, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+// grow a stream's previous-array buffer, preserving its content
+int cstream_reserve(b200lz4_cstream* s, uint32_t need)
+{
+    if (need <= s->dict_cap) return 0;
+    b200lz4_ctx* c = s->ctx;
+    uint32_t cap = need < 65536u ? 65536u : need;
+    uint8_t* nb = nullptr;
+    cudaError_t e = cudaMalloc(&nb, (size_t)cap + 16);
+    if (e != cudaSuccess) return fail(B200LZ4_E_NOMEM, std::string("cudaMalloc(dict): ") + cudaGetErrorString(e));
+    if (s->d_dict && s->last_len) CU(cudaMemcpyAsync(nb, s->d_dict, s->last_len, cudaMemcpyDeviceToDevice, c->stream));
+    int rc = set_dict_fields(s->d_state, nb, cap, c->stream);
+    if (rc) { cudaFree(nb); return rc; }
+    CU(cudaStreamSynchronize(c->stream));
+    if (s->d_dict) cudaFree(s->d_dict);
+    s->d_dict = nb; s->dict_cap = cap;
+    return 0;
+}
+
+int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
+                  const int64_t* src_off, const int32_t* src_len, int n,
+                  const int32_t* stream_first, int n_streams, b200lz4_cstream* const* streams,
+                  int accel, int header, const int32_t* block_cap,
+                  void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
+{
+    if (!c) return fail(B200LZ4_E_ARG, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!src_off || !src_len || !dst_off || !out_len))) return fail(B200LZ4_E_ARG, "NULL descriptor array");
+    if (header != 0 && header != 4 && header != 8) return fail(B200LZ4_E_ARG, "header_mode must be 0, 4 or 8");
+    if (streams && !stream_first) return fail(B200LZ4_E_ARG, "streams given without stream_first");
+    if (n == 0) { if (dst_off) dst_off[0] = 0; return 0; }
+    if (!src || !dst) return fail(B200LZ4_E_ARG, "NULL data buffer");
+    int rc;
+    if ((rc = check_blocks(src_off, src_len, n, src_bytes))) return rc;
+    if ((rc = check_streams(stream_first, n_streams, n))) return rc;
+    CU(cudaSetDevice(c->device));
+    const int ns = stream_first ? n_streams : n;
+
+    // stream state: make sure each persistent stream can keep its last array
+    if (streams) {
+        for (int s = 0; s < n_streams; s++) {
+            if (!streams[s] || streams[s]->ctx != c) return fail(B200LZ4_E_ARG, "stream handle belongs to another ctx");
+            if (stream_first[s + 1] > stream_first[s]) {
+                uint32_t need = (uint32_t)src_len[stream_first[s + 1] - 1];
+                if ((rc = cstream_reserve(streams[s], need))) return rc;
+            }
+        }
+    }
+
+    // descriptor block
+    Carver cv;
+    const size_t o_src_off = cv.take(sizeof(int64_t) * n);
+    const size_t o_slot_off = cv.take(sizeof(int64_t) * n);
+    const size_t o_src_len = cv.take(sizeof(int32_t) * n);
+    const size_t o_cap = cv.take(sizeof(int32_t) * n);
+    const size_t o_first = cv.take(sizeof(int32_t) * (ns + 1));
+    const size_t o_states = cv.take(sizeof(void*) * ns);
+    const size_t o_upload_end = cv.off;
+    const size_t o_out_len = cv.take(sizeof(int32_t) * n);
+    const size_t o_out_off = cv.take(sizeof(int64_t) * (n + 1));
+    const size_t desc_bytes = cv.off;
+    if ((rc = c->h_desc.ensure(desc_bytes))) return rc;
+    if ((rc = c->d_desc.ensure(desc_bytes))) return rc;
+    uint8_t* hd = static_cast<uint8_t*>(c->h_desc.p);
+    uint8_t* dd = static_cast<uint8_t*>(c->d_desc.p);
+    int64_t* h_slot_off = reinterpret_cast<int64_t*>(hd + o_slot_off);
+    int32_t* h_cap = reinterpret_cast<int32_t*>(hd + o_cap);
+    memcpy(hd + o_src_off, src_off, sizeof(int64_t) * n);
+    memcpy(hd + o_src_len, src_len, sizeof(int32_t) * n);
+    int64_t slots_total = 0;
+    for (int i = 0; i < n; i++) {
+        int cap = block_cap ? block_cap[i] : bound_of(src_len[i]);
+        if (cap < 0) cap = 0;
+        h_cap[i] = cap + header;
+        h_slot_off[i] = slots_total;
+        slots_total += align16((int64_t)cap + header + 16);
+    }
+    if (stream_first) memcpy(hd + o_first, stream_first, sizeof(int32_t) * (ns + 1));
+    if (streams) { void** hs = reinterpret_cast<void**>(hd + o_states); for (int s = 0; s < ns; s++) hs[s] = streams[s]->d_state; }
+
+    if ((rc = c->d_src.ensure((size_t)src_bytes + 64))) return rc;
+    if ((rc = c->d_slots.ensure((size_t)slots_total + 64))) return rc;
+    if ((rc = c->d_out.ensure((size_t)slots_total + 64))) return rc;
+
+    cudaStream_t st = c->stream;
+    CU(cudaEventRecord(c->ev[0], st));
+    if (src_bytes) CU(cudaMemcpyAsync(c->d_src.p, src, (size_t)src_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dd, hd, o_upload_end, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->ev[1], st));
+
+    CompressArgs a{};
+    a.src = static_cast<const uint8_t*>(c->d_src.p);
+    a.src_off = reinterpret_cast<const int64_t*>(dd + o_src_off);
+    a.src_len = reinterpret_cast<const int32_t*>(dd + o_src_len);
+    a.n_blocks = n;
+    a.stream_first = stream_first ? reinterpret_cast<const int32_t*>(dd + o_first) : nullptr;
+    a.n_streams = ns;
+    a.states = streams ? reinterpret_cast<void* const*>(dd + o_states) : nullptr;
+    a.dst = static_cast<uint8_t*>(c->d_slots.p);
+    a.dst_off = reinterpret_cast<const int64_t*>(dd + o_slot_off);
+    a.dst_cap = block_cap ? reinterpret_cast<const int32_t*>(dd + o_cap) : nullptr;
+    a.out_len = reinterpret_cast<int32_t*>(dd + o_out_len);
+    a.accel = accel; a.header = header; a.scratch = c->scratch;
+    CU(launch_compress(a, st));
+    CompactArgs g{a.dst, a.dst_off, a.out_len, n, header, static_cast<uint8_t*>(c->d_out.p),
+                  reinterpret_cast<int64_t*>(dd + o_out_off)};
+    CU(launch_compact(g, st));
+    c->launches += kernel_launches_per_compress() + kernel_launches_per_compact();
+    CU(cudaEventRecord(c->ev[2], st));
+    CU(cudaMemcpyAsync(hd + o_out_len, dd + o_out_len, desc_bytes - o_out_len, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int32_t* h_out_len = reinterpret_cast<const int32_t*>(hd + o_out_len);
+    const int64_t* h_out_off = reinterpret_cast<const int64_t*>(hd + o_out_off);
+    const int64_t total = h_out_off[n];
+    memcpy(out_len, h_out_len, sizeof(int32_t) * n);
+    memcpy(dst_off, h_out_off, sizeof(int64_t) * (n + 1));
+    if (total > dst_cap) return fail(B200LZ4_E_NOMEM, "dst_cap too small: need " + std::to_string(total));
+    if (total) CU(cudaMemcpyAsync(dst, c->d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(c->ev[3], st));
+    CU(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->t_kernel, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->t_d2h, c->ev[2], c->ev[3]);
+    if (streams) for (int s = 0; s < n_streams; s++)
+        if (stream_first[s + 1] > stream_first[s]) streams[s]->last_len = (uint32_t)src_len[stream_first[s + 1] - 1];
+    for (int i = 0; i < n; i++) if (out_len[i] <= 0) return fail(B200LZ4_E_BLOCK, "block " + std::to_string(i) + " failed to compress");
+    return 0;
+}
+
+inline int32_t le32(const uint8_t* p)
+{ return (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24)); }
+
+int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
+                    const int64_t* src_off, const int32_t* src_len, int n,
+                    const int32_t* stream_first, int n_streams, b200lz4_dstream* const* streams,
+                    int header, int max_block,
+                    void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
+{
+    if (!c) return fail(B200LZ4_E_ARG, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!src_off || !src_len || !dst_off || !out_len))) return fail(B200LZ4_E_ARG, "NULL descriptor array");
+    if (header != 0 && header != 4 && header != 8) return fail(B200LZ4_E_ARG, "header_mode must be 0, 4 or 8");
+    if (header != 8 && max_block < 0) return fail(B200LZ4_E_ARG, "max_block");
+    if (streams && !stream_first) return fail(B200LZ4_E_ARG, "streams given without stream_first");
+    if (n == 0) { if (dst_off) dst_off[0] = 0; return 0; }
+    if (!src || !dst) return fail(B200LZ4_E_ARG, "NULL data buffer");
+    int rc;
+    if ((rc = check_blocks(src_off, src_len, n, src_bytes))) return rc;
+    if ((rc = check_streams(stream_first, n_streams, n))) return rc;
+    CU(cudaSetDevice(c->device));
+    const int ns = stream_first ? n_streams : n;
+    if (streams) for (int s = 0; s < n_streams; s++)
+        if (!streams[s] || streams[s]->ctx != c) return fail(B200LZ4_E_ARG, "stream handle belongs to another ctx");
+
+    Carver cv;
+    const size_t o_src_off = cv.take(sizeof(int64_t) * n);
+    const size_t o_slot_off = cv.take(sizeof(int64_t) * n);
+    const size_t o_src_len = cv.take(sizeof(int32_t) * n);
+    const size_t o_cap = cv.take(sizeof(int32_t) * n);
+    const size_t o_first = cv.take(sizeof(int32_t) * (ns + 1));
+    const size_t o_states = cv.take(sizeof(void*) * ns);
+    const size_t o_upload_end = cv.off;
+    const size_t o_out_len = cv.take(sizeof(int32_t) * n);
+    const size_t o_out_off = cv.take(sizeof(int64_t) * (n + 1));
+    const size_t desc_bytes = cv.off;
+    if ((rc = c->h_desc.ensure(desc_bytes))) return rc;
+    if ((rc = c->d_desc.ensure(desc_bytes))) return rc;
+    uint8_t* hd = static_cast<uint8_t*>(c->h_desc.p);
+    uint8_t* dd = static_cast<uint8_t*>(c->d_desc.p);
+    int64_t* h_slot_off = reinterpret_cast<int64_t*>(hd + o_slot_off);
+    int32_t* h_cap = reinterpret_cast<int32_t*>(hd + o_cap);
+    memcpy(hd + o_src_off, src_off, sizeof(int64_t) * n);
+    memcpy(hd + o_src_len, src_len, sizeof(int32_t) * n);
+    // capacities: the header's uncompLen (BlockHasSize) or the configured maximum (LZ4.hs:189-198)
+    const uint8_t* hsrc = static_cast<const uint8_t*>(src);
+    int64_t slots_total = 0;
+    for (int i = 0; i < n; i++) {
+        int cap = max_block;
+        if (header == 8) cap = src_len[i] >= 8 ? le32(hsrc + src_off[i] + 4) : 0;
+        if (cap < 0) cap = 0;
+        h_cap[i] = cap;
+        h_slot_off[i] = slots_total;
+        slots_total += (header == 8) ? (int64_t)cap : align16((int64_t)cap);
+    }
+    const bool contiguous = (header == 8);     // slots are already exactly the output layout
+    if (contiguous && slots_total > dst_cap) return fail(B200LZ4_E_NOMEM, "dst_cap too small: need " + std::to_string(slots_total));
+    if (stream_first) memcpy(hd + o_first, stream_first, sizeof(int32_t) * (ns + 1));
+    if (streams) { void** hs = reinterpret_cast<void**>(hd + o_states); for (int s = 0; s < ns; s++) hs[s] = streams[s]->d_state; }
+
+    if ((rc = c->d_src.ensure((size_t)src_bytes + 64))) return rc;
+    if ((rc = c->d_slots.ensure((size_t)slots_total + 64))) return rc;
+    if (!contiguous && (rc = c->d_out.ensure((size_t)slots_total + 64))) return rc;
+
+    cudaStream_t st = c->stream;
+    CU(cudaEventRecord(c->ev[0], st));
+    if (src_bytes) CU(cudaMemcpyAsync(c->d_src.p, src, (size_t)src_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dd, hd, o_upload_end, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->ev[1], st));
+
+    DecompressArgs a{};
+    a.src = static_cast<const uint8_t*>(c->d_src.p);
+    a.src_off = reinterpret_cast<const int64_t*>(dd + o_src_off);
+    a.src_len = reinterpret_cast<const int32_t*>(dd + o_src_len);
+    a.n_blocks = n;
+    a.stream_first = stream_first ? reinterpret_cast<const int32_t*>(dd + o_first) : nullptr;
+    a.n_streams = ns;
+    a.states = streams ? reinterpret_cast<void* const*>(dd + o_states) : nullptr;
+    a.dst = static_cast<uint8_t*>(c->d_slots.p);
+    a.dst_off = reinterpret_cast<const int64_t*>(dd + o_slot_off);
+    a.dst_cap = reinterpret_cast<const int32_t*>(dd + o_cap);
+    a.out_len = reinterpret_cast<int32_t*>(dd + o_out_len);
+    a.header = header; a.max_block = max_block; a.scratch = c->scratch;
+    CU(launch_decompress(a, st));
+    c->launches += kernel_launches_per_decompress();
+    const uint8_t* d_result = a.dst;
+    if (!contiguous) {
+        CompactArgs g{a.dst, a.dst_off, a.out_len, n, 0, static_cast<uint8_t*>(c->d_out.p),
+                      reinterpret_cast<int64_t*>(dd + o_out_off)};
+        CU(launch_compact(g, st));
+        c->launches += kernel_launches_per_compact();
+        d_result = g.out;
+    }
+    CU(cudaEventRecord(c->ev[2], st));
+    CU(cudaMemcpyAsync(hd + o_out_len, dd + o_out_len, desc_bytes - o_out_len, cudaMemcpyDeviceToHost, st));
+    int64_t total = slots_total;
+    if (!contiguous) {
+        CU(cudaStreamSynchronize(st));
+        total = reinterpret_cast<const int64_t*>(hd + o_out_off)[n];
+        if (total > dst_cap) return fail(B200LZ4_E_NOMEM, "dst_cap too small: need " + std::to_string(total));
+    }
+    if (total) CU(cudaMemcpyAsync(dst, d_result, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(c->ev[3], st));
+    CU(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->t_kernel, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->t_d2h, c->ev[2], c->ev[3]);
+    memcpy(out_len, hd + o_out_len, sizeof(int32_t) * n);
+    if (contiguous) { memcpy(dst_off, h_slot_off, sizeof(int64_t) * n); dst_off[n] = slots_total; }
+    else memcpy(dst_off, hd + o_out_off, sizeof(int64_t) * (n + 1));
+    for (int i = 0; i < n; i++) if (out_len[i] < 0) return fail(B200LZ4_E_BLOCK, "block " + std::to_string(i) + " failed to decompress");
+    return 0;
+}
+
+}  // namespace
+
+// ============================================================== C ABI ====
+
+extern "C" {
+
+int b200lz4_compress_bound(int n) { return bound_of(n); }
+int b200lz4_version(void) { return B200LZ4_VERSION_NUMBER; }
+const char* b200lz4_last_error(void) { return g_err.c_str(); }
+
+int b200lz4_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+int b200lz4_ctx_create(int device, b200lz4_ctx** out)
+{
+    if (!out) return fail(B200LZ4_E_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(B200LZ4_E_CUDA, "no CUDA device: this library has no CPU path"); }
+    if (device < 0 || device >= n) return fail(B200LZ4_E_ARG, "device index out of range");
+    int major = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(B200LZ4_E_CUDA, "device is not compute capability 10.x (kernels are built for sm_100a only)");
+    CU(cudaSetDevice(device));
+    b200lz4_ctx* c = new (std::nothrow) b200lz4_ctx();
+    if (!c) return fail(B200LZ4_E_NOMEM, "out of host memory");
+    c->device = device;
+    cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&c->scratch, sizeof(Scratch));
+    if (e2 == cudaSuccess) e2 = cudaMemset(c->scratch, 0, sizeof(Scratch));
+    for (int i = 0; i < 4 && e2 == cudaSuccess; i++) e2 = cudaEventCreate(&c->ev[i]);
+    if (e2 != cudaSuccess) { b200lz4_ctx_destroy(c); return fail_cuda(e2, "ctx_create"); }
+    *out = c;
+    return 0;
+}
+
+void b200lz4_ctx_destroy(b200lz4_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->d_src.release(); c->d_slots.release(); c->d_out.release(); c->d_desc.release(); c->h_desc.release();
+    if (c->scratch) cudaFree(c->scratch);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* b200lz4_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail_cuda(e, "cudaMallocHost"); return nullptr; }
+    return p;
+}
+void b200lz4_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int b200lz4_last_timing(b200lz4_ctx* c, float* h2d, float* kern, float* d2h)
+{
+    if (!c) return fail(B200LZ4_E_ARG, "ctx is NULL");
+    if (h2d) *h2d = c->t_h2d;
+    if (kern) *kern = c->t_kernel;
+    if (d2h) *d2h = c->t_d2h;
+    return 0;
+}
+int64_t b200lz4_launch_count(b200lz4_ctx* c) { return c ? c->launches : 0; }
+
+int b200lz4_cstream_create(b200lz4_ctx* c, b200lz4_cstream** out)
+{
+    if (!c || !out) return fail(B200LZ4_E_ARG, "NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    b200lz4_cstream* s = new (std::nothrow) b200lz4_cstream{c, nullptr, nullptr, 0, 0};
+    if (!s) return fail(B200LZ4_E_NOMEM, "out of host memory");
+    cudaError_t e = cudaMalloc(&s->d_state, sizeof(CState));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_state, 0, sizeof(CState), c->stream);     // LZ4_initStream, cbits/lz4.c:1443-1451
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { if (s->d_state) cudaFree(s->d_state); delete s; return fail_cuda(e, "cstream_create"); }
+    *out = s;
+    return 0;
+}
+void b200lz4_cstream_free(b200lz4_cstream* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->d_state) cudaFree(s->d_state);
+    if (s->d_dict) cudaFree(s->d_dict);
+    delete s;
+}
+int b200lz4_cstream_peek(b200lz4_cstream* s, uint32_t* table, uint32_t* offset)
+{
+    if (!s) return fail(B200LZ4_E_ARG, "NULL stream");
+    CU(cudaSetDevice(s->ctx->device));
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    if (table) CU(cudaMemcpy(table, s->d_state->table, sizeof(uint32_t) * kHashEntries, cudaMemcpyDeviceToHost));
+    if (offset) CU(cudaMemcpy(offset, &s->d_state->offset, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int b200lz4_dstream_create(b200lz4_ctx* c, b200lz4_dstream** out)
+{
+    if (!c || !out) return fail(B200LZ4_E_ARG, "NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    b200lz4_dstream* s = new (std::nothrow) b200lz4_dstream{c, nullptr};
+    if (!s) return fail(B200LZ4_E_NOMEM, "out of host memory");
+    cudaError_t e = cudaMalloc(&s->d_state, sizeof(DState));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_state, 0, 16, c->stream);                 // calloc, cbits/lz4.c:2265-2270
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { if (s->d_state) cudaFree(s->d_state); delete s; return fail_cuda(e, "dstream_create"); }
+    *out = s;
+    return 0;
+}
+void b200lz4_dstream_free(b200lz4_dstream* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->d_state) cudaFree(s->d_state);
+    delete s;
+}
+
+int b200lz4_compress_batch(b200lz4_ctx* c, const void* src, int64_t src_bytes,
+                           const int64_t* src_off, const int32_t* src_len, int n_blocks,
+                           const int32_t* stream_first, int n_streams, b200lz4_cstream* const* streams,
+                           int acceleration, int header_mode,
+                           void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
+{
+    return compress_host(c, src, src_bytes, src_off, src_len, n_blocks, stream_first, n_streams, streams,
+                         acceleration, header_mode, nullptr, dst, dst_cap, dst_off, out_len);
+}
+
+int b200lz4_decompress_batch(b200lz4_ctx* c, const void* src, int64_t src_bytes,
+                             const int64_t* src_off, const int32_t* src_len, int n_blocks,
+                             const int32_t* stream_first, int n_streams, b200lz4_dstream* const* streams,
+                             int header_mode, int max_block,
+                             void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
+{
+    return decompress_host(c, src, src_bytes, src_off, src_len, n_blocks, stream_first, n_streams, streams,
+                           header_mode, max_block, dst, dst_cap, dst_off, out_len);
+}
+
+// ---------------------------------------------------------------- device path
+
+size_t b200lz4_cstate_bytes(void) { return sizeof(CState); }
+size_t b200lz4_dstate_bytes(void) { return sizeof(DState); }
+size_t b200lz4_scratch_bytes(void) { return sizeof(Scratch); }
+
+int b200lz4_cstate_set_dict(void* d_state, void* d_dict_buf, uint32_t dict_cap, void* cuda_stream)
+{
+    if (!d_state) return fail(B200LZ4_E_ARG, "NULL state");
+    return set_dict_fields(static_cast<CState*>(d_state), static_cast<uint8_t*>(d_dict_buf), dict_cap,
+                           static_cast<cudaStream_t>(cuda_stream));
+}
+
+int b200lz4_compress_dev(const void* d_src, const int64_t* d_src_off, const int32_t* d_src_len, int n_blocks,
+                         const int32_t* d_stream_first, int n_streams, void* const* d_states,
+                         void* d_dst, const int64_t* d_dst_off, const int32_t* d_dst_cap, int32_t* d_out_len,
+                         int acceleration, int header_mode, void* d_scratch, void* cuda_stream)
+{
+    if (n_blocks < 0 || !d_scratch) return fail(B200LZ4_E_ARG, "bad argument");
+    if (header_mode != 0 && header_mode != 4 && header_mode != 8) return fail(B200LZ4_E_ARG, "header_mode must be 0, 4 or 8");
+    if (n_blocks == 0) return 0;
+    CompressArgs a{};
+    a.src = static_cast<const uint8_t*>(d_src); a.src_off = d_src_off; a.src_len = d_src_len; a.n_blocks = n_blocks;
+    a.stream_first = d_stream_first; a.n_streams = d_stream_first ? n_streams : n_blocks; a.states = d_states;
+    a.dst = static_cast<uint8_t*>(d_dst); a.dst_off = d_dst_off; a.dst_cap = d_dst_cap; a.out_len = d_out_len;
+    a.accel = acceleration; a.header = header_mode; a.scratch = static_cast<Scratch*>(d_scratch);
+    CU(launch_compress(a, static_cast<cudaStream_t>(cuda_stream)));
+    return 0;
+}
+
+int b200lz4_decompress_dev(const void* d_src, const int64_t* d_src_off, const int32_t* d_src_len, int n_blocks,
+                           const int32_t* d_stream_first, int n_streams, void* const* d_states,
+                           void* d_dst, const int64_t* d_dst_off, const int32_t* d_dst_cap, int32_t* d_out_len,
+                           int header_mode, int max_block, void* d_scratch, void* cuda_stream)
+{
+    if (n_blocks < 0 || !d_scratch) return fail(B200LZ4_E_ARG, "bad argument");
+    if (header_mode != 0 && header_mode != 4 && header_mode != 8) return fail(B200LZ4_E_ARG, "header_mode must be 0, 4 or 8");
+    if (n_blocks == 0) return 0;
+    DecompressArgs a{};
+    a.src = static_cast<const uint8_t*>(d_src); a.src_off = d_src_off; a.src_len = d_src_len; a.n_blocks = n_blocks;
+    a.stream_first = d_stream_first; a.n_streams = d_stream_first ? n_streams : n_blocks; a.states = d_states;
+    a.dst = static_cast<uint8_t*>(d_dst); a.dst_off = d_dst_off; a.dst_cap = d_dst_cap; a.out_len = d_out_len;
+    a.header = header_mode; a.max_block = max_block; a.scratch = static_cast<Scratch*>(d_scratch);
+    CU(launch_decompress(a, static_cast<cudaStream_t>(cuda_stream)));
+    return 0;
+}
+
+int b200lz4_compact_dev(const void* d_slots, const int64_t* d_slot_off, const int32_t* d_len, int n_blocks,
+                        int header_mode, void* d_out, int64_t* d_out_off, void* d_scratch, void* cuda_stream)
+{
+    (void)d_scratch;
+    if (n_blocks < 0) return fail(B200LZ4_E_ARG, "bad argument");
+    CompactArgs g{static_cast<const uint8_t*>(d_slots), d_slot_off, d_len, n_blocks, header_mode,
+                  static_cast<uint8_t*>(d_out), d_out_off};
+    CU(launch_compact(g, static_cast<cudaStream_t>(cuda_stream)));
+    return 0;
+}
+
+// ------------------------------------------------------------------ re-frame
+// resizeChunksD's `process` (src/Streamly/Internal/LZ4.hs:459-484) applied to one contiguous range.
+int b200lz4_reframe(const void* buf, int64_t len, int header_mode, int has_end_mark,
+                    int64_t* block_off, int32_t* block_len, int64_t max_blocks,
+                    int64_t* n_found, int64_t* consumed, int* ended)
+{
+    if (!n_found || !consumed || len < 0 || (len > 0 && !buf)) return fail(B200LZ4_E_ARG, "NULL argument");
+    if (header_mode != 4 && header_mode != 8) return fail(B200LZ4_E_ARG, "header_mode must be 4 or 8");
+    const uint8_t* p = static_cast<const uint8_t*>(buf);
+    int64_t at = 0, k = 0;
+    if (ended) *ended = 0;
+    *n_found = 0; *consumed = 0;
+    while (k < max_blocks) {
+        int64_t rest = len - at;
+        if (rest < 4) break;                                            // LZ4.hs:461-462
+        int32_t comp = le32(p + at);
+        if (has_end_mark && comp == 0) {                                // LZ4.hs:464-466 -> RFooter; footer is the 4 bytes themselves
+            at += 4; if (ended) *ended = 1; break;
+        }
+        if (rest <= header_mode) break;                                 // LZ4.hs:468-469
+        if (comp <= 0) { *n_found = k; *consumed = at; return fail(B200LZ4_E_FRAME, "block header with compLen <= 0"); }
+        int64_t required = (int64_t)comp + header_mode;                 // LZ4.hs:474
+        if (rest < required) break;                                     // LZ4.hs:477-478 (RAccumulate)
+        if (block_off) block_off[k] = at;
+        if (block_len) block_len[k] = (int32_t)required;
+        k++; at += required;                                            // LZ4.hs:475-476, :479-484
+    }
+    *n_found = k; *consumed = at;
+    return 0;
+}
+
+// ------------------------------------------------------------ legacy aliases
+
+struct LZ4_stream_u { b200lz4_cstream* s; };
+struct LZ4_streamDecode_u { b200lz4_dstream* s; };
+
+static std::mutex g_legacy_mu;
+static b200lz4_ctx* g_legacy_ctx = nullptr;
+static b200lz4_ctx* legacy_ctx()
+{
+    if (!g_legacy_ctx) {
+        int dev = 0;
+        if (const char* e = getenv("B200LZ4_DEVICE")) dev = atoi(e);
+        if (b200lz4_ctx_create(dev, &g_legacy_ctx) != 0) {
+            fprintf(stderr, "libb200lz4: %s\n", g_err.c_str());
+            return nullptr;
+        }
+    }
+    return g_legacy_ctx;
+}
+
+LZ4_stream_t* LZ4_createStream(void)
+{
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    b200lz4_ctx* c = legacy_ctx();
+    if (!c) return nullptr;
+    LZ4_stream_u* h = new (std::nothrow) LZ4_stream_u{nullptr};
+    if (!h) return nullptr;
+    if (b200lz4_cstream_create(c, &h->s) != 0) { delete h; return nullptr; }
+    return h;
+}
+int LZ4_freeStream(LZ4_stream_t* h)
+{
+    if (!h) return 0;
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    b200lz4_cstream_free(h->s); delete h;
+    return 0;
+}
+LZ4_streamDecode_t* LZ4_createStreamDecode(void)
+{
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    b200lz4_ctx* c = legacy_ctx();
+    if (!c) return nullptr;
+    LZ4_streamDecode_u* h = new (std::nothrow) LZ4_streamDecode_u{nullptr};
+    if (!h) return nullptr;
+    if (b200lz4_dstream_create(c, &h->s) != 0) { delete h; return nullptr; }
+    return h;
+}
+int LZ4_freeStreamDecode(LZ4_streamDecode_t* h)
+{
+    if (!h) return 0;
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    b200lz4_dstream_free(h->s); delete h;
+    return 0;
+}
+int LZ4_compressBound(int n) { return bound_of(n); }
+
+int LZ4_compress_fast_continue(LZ4_stream_t* h, const char* src, char* dst, int srcSize, int dstCapacity, int acceleration)
+{
+    if (!h || !h->s || srcSize < 0 || !dst) return 0;
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    int64_t off = 0, dst_off[2] = {0, 0}; int32_t len = srcSize, out_len = 0, cap = dstCapacity, first[2] = {0, 1};
+    static const char empty = 0;
+    std::vector<char> tmp((size_t)bound_of(srcSize) + 16);
+    b200lz4_cstream* ss = h->s;
+    int rc = compress_host(ss->ctx, srcSize ? src : &empty, srcSize, &off, &len, 1, first, 1, &ss,
+                           acceleration, 0, &cap, tmp.data(), (int64_t)tmp.size(), dst_off, &out_len);
+    if (rc != 0 || out_len <= 0 || out_len > dstCapacity) return 0;
+    memcpy(dst, tmp.data(), (size_t)out_len);
+    return out_len;
+}
+
+int LZ4_decompress_safe_continue(LZ4_streamDecode_t* h, const char* src, char* dst, int srcSize, int dstCapacity)
+{
+    if (!h || !h->s || !src || srcSize < 0 || dstCapacity < 0) return -1;
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    int64_t off = 0, dst_off[2] = {0, 0}; int32_t len = srcSize, out_len = -1, first[2] = {0, 1};
+    std::vector<char> tmp((size_t)dstCapacity + 16);
+    b200lz4_dstream* ss = h->s;
+    int rc = decompress_host(ss->ctx, src, srcSize, &off, &len, 1, first, 1, &ss, 0, dstCapacity,
+                             tmp.data(), (int64_t)tmp.size(), dst_off, &out_len);
+    if (rc != 0 && rc != B200LZ4_E_BLOCK) return -1;
+    if (out_len > 0) memcpy(dst, tmp.data() + dst_off[0], (size_t)out_len);
+    return out_len;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// compact.cu -- compaction pass: exclusive scan of framed block sizes, then a gather of the
+// per-block slots into one contiguous stream (so D2H moves only real bytes and the host can
+// slice arrays straight out of the result, headers already in place).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200lz4 {
+
+namespace {
+
+constexpr int kScanThreads = 1024;
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(const int32_t* __restrict__ len, int n, int header, int64_t* __restrict__ out_off)
+{
+    __shared__ long long partial[kScanThreads];
+    const int t = threadIdx.x;
+    const int per = (n + kScanThreads - 1) / kScanThreads;
+    const int lo = min(t * per, n), hi = min(lo + per, n);
+    long long sum = 0;
+    for (int i = lo; i < hi; i++) { int l = len[i]; sum += (l > 0) ? (long long)(l + header) : 0; }
+    partial[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < kScanThreads; d <<= 1) {       // Hillis-Steele inclusive scan
+        long long v = (t >= d) ? partial[t - d] : 0;
+        __syncthreads();
+        partial[t] += v;
+        __syncthreads();
+    }
+    long long run = partial[t] - sum;                   // exclusive prefix of this thread's chunk
+    for (int i = lo; i < hi; i++) { out_off[i] = run; int l = len[i]; run += (l > 0) ? (long long)(l + header) : 0; }
+    if (t == kScanThreads - 1) out_off[n] = partial[t];
+}
+
+constexpr int kGatherThreads = 256;
+
+__global__ void __launch_bounds__(kGatherThreads)
+gather_kernel(CompactArgs a)
+{
+    const uint32_t t = threadIdx.x;
+    for (int b = blockIdx.x; b < a.n_blocks; b += gridDim.x) {
+        const int l = a.len[b];
+        if (l <= 0) continue;
+        uint32_t n = (uint32_t)(l + a.header);
+        const uint8_t* src = a.slots + a.slot_off[b];
+        uint8_t* dst = a.out + a.out_off[b];
+        uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+        if (head > n) head = n;
+        if (t < head) dst[t] = __ldg(src + t);
+        src += head; dst += head; n -= head;
+        const uint32_t nvec = n >> 4;
+        uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+        const uint32_t sh = (uint32_t)(sa & 3) * 8;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+        uint4* dv = reinterpret_cast<uint4*>(dst);
+        if ((sa & 15) == 0) {
+            const uint4* sv = reinterpret_cast<const uint4*>(src);
+            for (uint32_t v = t; v < nvec; v += kGatherThreads) dv[v] = __ldg(sv + v);
+        } else if (sh == 0) {
+            for (uint32_t v = t; v < nvec; v += kGatherThreads) {
+                const uint32_t* q = sw + 4 * v;
+                dv[v] = make_uint4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+            }
+        } else {
+            for (uint32_t v = t; v < nvec; v += kGatherThreads) {
+                const uint32_t* q = sw + 4 * v;
+                uint32_t x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2), x3 = __ldg(q + 3), x4 = __ldg(q + 4);
+                dv[v] = make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh),
+                                   __funnelshift_r(x2, x3, sh), __funnelshift_r(x3, x4, sh));
+            }
+        }
+        const uint32_t done = nvec << 4, tail = n - done;
+        if (t < tail) dst[done + t] = __ldg(src + done + t);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_compact(const CompactArgs& a, cudaStream_t stream)
+{
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
+    }
+    scan_kernel<<<1, kScanThreads, 0, stream>>>(a.len, a.n_blocks, a.header, a.out_off);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || a.n_blocks <= 0) return e;
+    int grid = a.n_blocks < sm_count * 8 ? a.n_blocks : sm_count * 8;
+    gather_kernel<<<grid, kGatherThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+int kernel_launches_per_compress() { return 1; }
+int kernel_launches_per_decompress() { return 1; }
+int kernel_launches_per_compact() { return 2; }
+
+}  // namespace b200lz4

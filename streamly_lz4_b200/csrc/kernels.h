@@ -1,0 +1,37 @@
+// kernels.h -- launch interfaces between the C ABI (api.cu) and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace b200lz4 {
+
+struct CompressArgs {
+    const uint8_t* src; const int64_t* src_off; const int32_t* src_len; int n_blocks;
+    const int32_t* stream_first; int n_streams; void* const* states;
+    uint8_t* dst; const int64_t* dst_off; const int32_t* dst_cap; int32_t* out_len;
+    int accel; int header;
+    Scratch* scratch;
+};
+
+struct DecompressArgs {
+    const uint8_t* src; const int64_t* src_off; const int32_t* src_len; int n_blocks;
+    const int32_t* stream_first; int n_streams; void* const* states;
+    uint8_t* dst; const int64_t* dst_off; const int32_t* dst_cap; int32_t* out_len;
+    int header; int max_block;
+    Scratch* scratch;
+};
+
+struct CompactArgs {
+    const uint8_t* slots; const int64_t* slot_off; const int32_t* len; int n_blocks;
+    int header; uint8_t* out; int64_t* out_off;
+};
+
+cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream);
+cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream);
+cudaError_t launch_compact(const CompactArgs& a, cudaStream_t stream);
+int kernel_launches_per_compress();
+int kernel_launches_per_decompress();
+int kernel_launches_per_compact();
+
+}  // namespace b200lz4
