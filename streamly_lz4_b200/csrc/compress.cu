@@ -2,21 +2,34 @@
 //
 // Reproduces LZ4_compress_fast_continue in external-dictionary mode
 // (cbits/lz4.c:1565-1637 -> LZ4_compress_generic_validated :851-1240 with
-// limitedOutput/byU32/usingExtDict) bit for bit, but is organised for a SIMT machine:
+// limitedOutput/byU32/usingExtDict) bit for bit, organised for a SIMT machine.
 //
-//   * one WARP owns one stream (independent mode: one block) and keeps the 16 KiB
-//     position table in shared memory for the whole stream;
-//   * the serial "probe, overwrite, test" recurrence of the match finder
-//     (cbits/lz4.c:959-1014) is evaluated 32 probes at a time: the probe positions of
-//     a search run follow a closed-form schedule (step_k = (acc*64 + k - 1) >> 6), so
-//     lane l speculatively evaluates probe j0+l; same-bucket forwarding inside the
-//     window is resolved with __match_any_sync (a lane's candidate is the nearest
-//     lower lane with the same hash, else the table), the lowest accepting lane wins,
-//     lanes up to the winner commit their table writes in order (last writer per
-//     bucket wins), later lanes are discarded;
-//   * the post-match re-test at ip (cbits/lz4.c:1159-1196) rides in the same window
-//     as probe index -1 of the next run;
-//   * catch-up, match-length counting and literal copies are warp-parallel.
+// One stream (independent mode: one block) is owned by a PAIR of warps:
+//
+//   FINDER warp  -- runs the match finder, the only inherently serial part.  It keeps the
+//     16 KiB position table in shared memory and produces (literal run, match length,
+//     offset) triples.
+//       * After a match the reference inserts ip-2 and immediately re-tests ip
+//         (cbits/lz4.c:1146-1196).  This "match follows match" regime dominates
+//         compressible data, so it is a warp-uniform scalar path: one broadcast load of
+//         the bytes around ip, two hashes, one table read/write, then ONE 32-lane
+//         load that both verifies the 4-byte candidate and counts the match length.
+//       * Otherwise the serial "probe, overwrite, test" recurrence (cbits/lz4.c:959-1014)
+//         is evaluated up to 32 probes at a time.  Probe positions follow a closed-form
+//         schedule (step_k = (acc*64 + k - 1) >> 6), lane l speculatively evaluates probe
+//         j0+l; same-bucket forwarding inside the window is resolved with
+//         __match_any_sync (a lane's candidate is the nearest lower lane with the same
+//         hash, else the table), the lowest accepting lane wins, lanes up to the winner
+//         commit their table writes in order (last writer per bucket wins), later lanes
+//         are discarded.  The window width adapts (4 or 32) so that large accelerations
+//         do not touch far cache lines that the serial algorithm would never read.
+//       * upcoming input is pulled into L2 with cp.async.bulk.prefetch.L2.
+//   EMITTER warp -- receives the triples through a double-buffered shared-memory queue
+//     (mbarrier full/empty handshakes), turns 32 of them at a time into LZ4 sequences:
+//     encoded sizes -> warp prefix sum -> every lane writes its own token / length bytes /
+//     offset, literal runs are copied per lane (short) or cooperatively (long, 128-bit).
+//
+// The compaction pass (compact.cu) then gathers the per-block slots into one stream.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -24,205 +37,280 @@ namespace b200lz4 {
 
 namespace {
 
-struct BlockIn {
-    const uint8_t* src; int n;
-    const uint8_t* dict_end;    // one past the last dictionary byte (valid iff dict_len > 0)
-    uint32_t dict_len;
-    uint32_t start;             // currentOffset before this block
-    uint8_t* dst; int cap;
-    int accel;
-};
+constexpr int kPairs = 4;                        // stream-owning warp pairs per CTA
+constexpr int kQueueDepth = 32;                  // descriptors per queue buffer
+constexpr uint32_t kPrefetchAhead = 16384;       // bytes of input kept ahead in L2
+constexpr uint32_t kPrefetchChunk = 4096;
 
-// offset (from the run start) and step of probe j >= -1 of a search run.
+struct __align__(16) Queue {
+    uint4 desc[2][kQueueDepth];                  // {literal start, literal length, match code, offset (0 = final literals)}
+    unsigned long long full[2], empty[2];        // mbarriers
+    int count[2];                                // descriptors in buffer; bit 30 = block ends here, bit 29 = terminate
+    int block[2];                                // block index the buffer belongs to
+    int pad_[4];
+};
+constexpr int kEndBlock = 1 << 30, kTerminate = 1 << 29;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes)
+{ asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
+
+// offset (from the run start) and step of probe j >= 0 of a search run (cbits/lz4.c:957-967).
 __device__ __forceinline__ void probe_schedule(long long j, int accel, long long& off, int& step)
 {
-    if (j <= 0) { off = j; step = 1; return; }       // j == -1: the re-test position; j == 0: run start
+    if (j <= 0) { off = 0; step = 1; return; }
     long long m = j - 1, q = m >> 6, r = m & 63;
     off = 1 + m * accel + 32 * q * (q - 1) + q * r;
     step = accel + (int)q;
 }
 
-// common-prefix length of a[0..cap) and b[0..cap); a, b read-only global. Warp-parallel,
-// 4 bytes per lane per round. (What LZ4_count returns, cbits/lz4.c:603-626.)
+// Common-prefix length of a[0..cap) and b[0..cap), 4 bytes per lane per round (what LZ4_count
+// computes, cbits/lz4.c:603-626).  a, b read-only global memory.
 __device__ __forceinline__ uint32_t warp_common_prefix(const uint8_t* a, const uint8_t* b, uint32_t cap)
 {
     const uint32_t lane = lane_id();
     uint32_t base = 0;
     for (;;) {
-        uint32_t at = base + lane * 4;
-        uint32_t nb = 0;            // equal bytes in this lane's chunk
+        const uint32_t at = base + lane * 4;
+        uint32_t nb = 0;
         bool stop = true;
-        if (at < cap) {
-            uint32_t room = cap - at;
-            if (room >= 4) {
-                uint32_t x = ldg_u32_unaligned(a + at) ^ ldg_u32_unaligned(b + at);
-                nb = x ? ((uint32_t)(__ffs(x) - 1) >> 3) : 4u;
-                stop = (nb < 4);
-            } else {
-                while (nb < room && __ldg(a + at + nb) == __ldg(b + at + nb)) nb++;
-                stop = true;
-            }
+        if (at + 4 <= cap) {
+            uint32_t x = ldg_u32_unaligned(a + at) ^ ldg_u32_unaligned(b + at);
+            nb = x ? ((uint32_t)(__ffs(x) - 1) >> 3) : 4u;
+            stop = (nb < 4);
+        } else if (at < cap) {
+            const uint32_t room = cap - at;
+            while (nb < room && __ldg(a + at + nb) == __ldg(b + at + nb)) nb++;
         }
-        uint32_t sb = __ballot_sync(kFull, stop);
+        const uint32_t sb = __ballot_sync(kFull, stop);
         if (sb) {
-            int l = __ffs(sb) - 1;
-            uint32_t res = __shfl_sync(kFull, at + nb, l);
+            const int l = __ffs(sb) - 1;
+            const uint32_t res = __shfl_sync(kFull, at + nb, l);
             return res < cap ? res : cap;
         }
         base += 128;
     }
 }
 
-__device__ __forceinline__ void emit_len_ext(uint8_t* op, uint32_t rest, uint32_t n_ext)
-{   // n_ext = rest/255 + 1 bytes: 255,255,...,rest%255
-    const uint32_t lane = lane_id();
-    for (uint32_t i = lane; i < n_ext; i += 32) op[i] = (i + 1 < n_ext) ? 255 : (uint8_t)(rest % 255);
-}
+struct BlockIn {
+    const uint8_t* src; int n;
+    const uint8_t* dict_end;    // one past the last dictionary byte (meaningful iff dict_len > 0)
+    uint32_t dict_len;
+    uint32_t start;             // currentOffset before this block
+    int accel;
+    int block;                  // block index (for the emitter)
+};
 
-// Encode one block. Returns compressed size (0 = does not fit `cap`).
-// `table` is this warp's shared-memory table; on return it holds the reference's table state.
-__device__ int encode_block(const BlockIn& in, uint32_t* table)
+// Producer side of the queue.
+struct Producer {
+    Queue* q;
+    uint32_t batch;     // batches pushed so far
+    int fill;           // descriptors in the current buffer
+
+    __device__ __forceinline__ void acquire()
+    {   // wait until the buffer we are about to fill has been drained
+        const uint32_t b = batch & 1, t = batch >> 1;
+        if (t) mbar_wait(&q->empty[b], (t - 1) & 1);
+    }
+    __device__ __forceinline__ void push(uint32_t lit_pos, uint32_t lit_len, uint32_t mcode, uint32_t off, int block)
+    {
+        if (fill == 0) acquire();
+        const uint32_t b = batch & 1;
+        if (lane_id() == 0) q->desc[b][fill] = make_uint4(lit_pos, lit_len, mcode, off);
+        fill++;
+        if (fill == kQueueDepth) flush(block, 0);
+    }
+    __device__ __forceinline__ void flush(int block, int flags)
+    {
+        if (fill == 0 && flags == 0) return;
+        if (fill == 0) acquire();
+        const uint32_t b = batch & 1;
+        if (lane_id() == 0) { q->count[b] = fill | flags; q->block[b] = block; }
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&q->full[b]);
+        batch++; fill = 0;
+    }
+};
+
+// Match finder for one block: pushes sequence descriptors, ends with the final-literals descriptor.
+__device__ void find_block(const BlockIn& in, uint32_t* table, Producer& out,
+                           const uint32_t off0, const uint32_t step0)
 {
     const uint32_t lane = lane_id();
     const uint8_t* const src = in.src;
     const int n = in.n;
-    uint8_t* const dst = in.dst;
     const uint32_t S = in.start;
     const bool dict_small = (in.dict_len < 65536u) && (in.dict_len < S);   // cbits/lz4.c:1627
     const uint32_t low_index = S - in.dict_len;                             // prefixIdxLimit, :879
     const int mfl = n - kMfLimit + 1;          // mflimitPlusOne as an index
     const int mlimit = n - kLastLiterals;      // matchlimit
-    long long op = 0;
     int anchor = 0;
 
     if (n >= kMinLength) {
+        uint32_t pf_next = 0;                  // next input byte not yet requested into L2
         if (lane == 0) { uint2 v = ldg_5bytes(src); table[hash5(v.x, v.y)] = S; }   // :924
         __syncwarp();
-        int run_start = 1;          // :925
-        bool retest = false;
+        int ip = 1;                            // :925  (search runs start here)
+        bool after_match = false;
+        bool narrow = false;                   // adaptive probe-window width
         for (;;) {
-            // ---------------- speculative probe window(s) ----------------
-            long long jbase = retest ? -1 : 0;
-            int mpos = 0; uint32_t midx = 0; bool found = false;
-            for (;;) {
-                long long j = jbase + lane, off; int step;
-                probe_schedule(j, in.accel, off, step);
-                long long pos64 = (long long)run_start + off;
-                bool valid = (j < 0) || (pos64 + step <= (long long)mfl);      // :969
-                uint32_t h = 0, seq = 0, cur = 0;
-                int pos = valid ? (int)pos64 : 0;
-                if (valid) {
-                    uint2 v = ldg_5bytes(src + pos);
-                    seq = v.x; h = hash5(v.x, v.y); cur = S + (uint32_t)pos;
-                }
-                uint32_t key = valid ? h : (0x1000u + lane);
-                uint32_t peers = __match_any_sync(kFull, key);
-                uint32_t lower = peers & lanemask_lt();
-                int from_lane = lower ? (31 - __clz(lower)) : (int)lane;
-                uint32_t fwd = __shfl_sync(kFull, cur, from_lane);
-                bool ok = false; uint32_t m = 0;
-                if (valid) {
-                    m = lower ? fwd : table[h];
-                    bool reach = !(dict_small && m < low_index) && (m + kMaxDistance >= cur);   // :1001-1006
-                    if (reach) {
-                        const uint8_t* c = (m < S) ? (in.dict_end - (S - m)) : (src + (m - S));   // :985-993
-                        ok = (ldg_u32_unaligned(c) == seq);                                     // :1009
+            // ---- keep the next kPrefetchAhead bytes of input on their way into L2
+            if (pf_next < (uint32_t)ip) pf_next = (uint32_t)ip & ~(kPrefetchChunk - 1);
+            if ((uint32_t)ip + kPrefetchAhead > pf_next && pf_next < (uint32_t)n) {
+                uintptr_t base = reinterpret_cast<uintptr_t>(src + pf_next) & ~uintptr_t(15);
+                uint32_t room = (uint32_t)n - pf_next;
+                uint32_t bytes = room < kPrefetchChunk ? (room & ~15u) : kPrefetchChunk;
+                if (lane == 0 && bytes) prefetch_l2_bulk(reinterpret_cast<const void*>(base), bytes);
+                pf_next += kPrefetchChunk;
+            }
+
+            int mpos; uint32_t midx; uint32_t mlen;     // match start, table index of its source, total length
+            bool have = false;
+            if (after_match) {
+                // ---- scalar path: put(ip-2), re-test ip (cbits/lz4.c:1146, :1159-1196); ip == anchor here
+                uintptr_t a = reinterpret_cast<uintptr_t>(src + ip - 2);
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+                const uint32_t sh = (uint32_t)(a & 3) * 8;
+                const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+                const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);   // bytes ip-2 .. ip+5
+                const uint32_t h2 = hash5(v0, v1 & 0xFFu);
+                const uint32_t seq = __funnelshift_r(v0, v1, 16);                                   // bytes ip .. ip+3
+                const uint32_t h = hash5(seq, (v1 >> 16) & 0xFFu);
+                const uint32_t cur = S + (uint32_t)ip;
+                // every lane performs the same three accesses in program order, so no warp sync is needed
+                table[h2] = cur - 2;                                                                 // :1146
+                const uint32_t m = table[h];
+                table[h] = cur;                                                                      // :1185
+                if (!(dict_small && m < low_index) && (m + kMaxDistance >= cur)) {                   // :1187-1188
+                    // verify + count in one 32-lane load: common prefix of ip.. and candidate..
+                    const bool in_dict = m < S;
+                    const uint8_t* cand = in_dict ? (in.dict_end - (S - m)) : (src + (m - S));
+                    uint32_t cap = (uint32_t)(mlimit - ip);
+                    if (in_dict) cap = min(cap, (uint32_t)(in.dict_end - cand));
+                    uint32_t L = warp_common_prefix(src + ip, cand, cap);
+                    if (L >= 4) {                                                                    // :1189
+                        if (in_dict && L == cap && (int)(ip + L) < mlimit)                           // :1085-1089
+                            L += warp_common_prefix(src + ip + L, src, (uint32_t)(mlimit - (ip + (int)L)));
+                        have = true; mpos = ip; midx = m; mlen = L;
                     }
                 }
-                uint32_t okb = __ballot_sync(kFull, ok);
-                uint32_t vb = __ballot_sync(kFull, valid);
-                int nvalid = __popc(vb);
-                int w = okb ? (__ffs(okb) - 1) : 32;
-                int ncommit = min(w + 1, nvalid);
-                if ((int)lane < ncommit) {              // ordered commit: last writer per bucket
-                    uint32_t grp = peers & (ncommit >= 32 ? kFull : ((1u << ncommit) - 1u));
-                    if ((31 - __clz(grp)) == (int)lane) table[h] = cur;     // :998
-                }
-                __syncwarp();
-                if (w < 32) { found = true; mpos = __shfl_sync(kFull, pos, w); midx = __shfl_sync(kFull, m, w); break; }
-                if (nvalid < 32) break;                 // ran into mflimit: last literals
-                jbase += 32;
+                if (!have) ip++;                                                                     // :1200
             }
-            if (!found) break;
+            if (!have) {
+                // ---- speculative probe windows (cbits/lz4.c:956-1014), run starts at ip
+                long long jbase = 0;
+                uint32_t width = narrow ? 4u : 32u;
+                bool found = false; int hit_index = 0;
+                for (;;) {
+                    long long off; int step;
+                    if (jbase == 0) { off = off0; step = (int)step0; }
+                    else probe_schedule(jbase + lane, in.accel, off, step);
+                    const long long pos64 = (long long)ip + off;
+                    const bool active = lane < width;
+                    const bool valid = active && (pos64 + step <= (long long)mfl);                   // :969
+                    uint32_t h = 0, seq = 0, cur = 0;
+                    const int pos = valid ? (int)pos64 : 0;
+                    if (valid) {
+                        uint2 v = ldg_5bytes(src + pos);
+                        seq = v.x; h = hash5(v.x, v.y); cur = S + (uint32_t)pos;
+                    }
+                    const uint32_t peers = __match_any_sync(kFull, valid ? h : (0x1000u + lane));
+                    const uint32_t lower = peers & lanemask_lt();
+                    const int from_lane = lower ? (31 - __clz(lower)) : (int)lane;
+                    const uint32_t fwd = __shfl_sync(kFull, cur, from_lane);
+                    bool ok = false; uint32_t m = 0;
+                    if (valid) {
+                        m = lower ? fwd : table[h];
+                        if (!(dict_small && m < low_index) && (m + kMaxDistance >= cur)) {           // :1001-1006
+                            const uint8_t* c = (m < S) ? (in.dict_end - (S - m)) : (src + (m - S));  // :985-993
+                            ok = (ldg_u32_unaligned(c) == seq);                                      // :1009
+                        }
+                    }
+                    const uint32_t okb = __ballot_sync(kFull, ok);
+                    const uint32_t vb = __ballot_sync(kFull, valid);
+                    const int nvalid = __popc(vb);                      // valid lanes form a prefix
+                    const int w = okb ? (__ffs(okb) - 1) : 32;
+                    const int ncommit = min(w + 1, nvalid);
+                    if ((int)lane < ncommit) {                          // ordered commit: last writer per bucket
+                        const uint32_t grp = peers & (ncommit >= 32 ? kFull : ((1u << ncommit) - 1u));
+                        if ((31 - __clz(grp)) == (int)lane) table[h] = cur;                          // :998
+                    }
+                    __syncwarp();
+                    if (w < 32) {
+                        found = true; hit_index = (int)jbase + w;
+                        mpos = __shfl_sync(kFull, pos, w); midx = __shfl_sync(kFull, m, w);
+                        break;
+                    }
+                    if (nvalid < (int)width) break;                     // ran into mflimit: last literals
+                    jbase += width;
+                    width = 32;
+                }
+                if (!found) break;
+                narrow = (in.accel > 16) && (hit_index < 3);
 
-            // ---------------- one sequence ----------------
-            int ip = mpos;
-            const uint32_t dist = (S + (uint32_t)ip) - midx;
-            const bool in_dict = midx < S;
-            const uint8_t* cand = in_dict ? (in.dict_end - (S - midx)) : (src + (midx - S));
-            {   // catch up, :1019
-                long long room_c = in_dict ? (long long)in.dict_len - (long long)(S - midx) : (long long)(midx - S);
-                long long maxback = min((long long)(ip - anchor), room_c);
-                long long back = 0;
-                while (back < maxback) {
-                    long long k = back + lane + 1;
-                    bool eq = (k <= maxback) && (__ldg(src + ip - k) == __ldg(cand - k));
-                    uint32_t b = __ballot_sync(kFull, eq);
-                    int run = (b == kFull) ? 32 : (__ffs(~b) - 1);
-                    back += run;
-                    if (run < 32) break;
+                // catch up (cbits/lz4.c:1019), then count (:1076-1095)
+                int mip = mpos;
+                const bool in_dict = midx < S;
+                const uint8_t* cand = in_dict ? (in.dict_end - (S - midx)) : (src + (midx - S));
+                {
+                    const uint32_t room_c = in_dict ? (in.dict_len - (S - midx)) : (midx - S);
+                    const uint32_t maxback = min((uint32_t)(mip - anchor), room_c);
+                    uint32_t back = 0;
+                    while (back < maxback) {
+                        const uint32_t k = back + lane + 1;
+                        const bool eq = (k <= maxback) && (__ldg(src + mip - k) == __ldg(cand - k));
+                        const uint32_t b = __ballot_sync(kFull, eq);
+                        const uint32_t run = (b == kFull) ? 32u : (uint32_t)(__ffs(~b) - 1);
+                        back += run;
+                        if (run < 32) break;
+                    }
+                    mip -= (int)back; cand -= back;
                 }
-                ip -= (int)back; cand -= back;
-            }
-            const uint32_t lit = (uint32_t)(ip - anchor);
-            // match length, :1076-1095
-            uint32_t mcode;
-            if (in_dict) {
-                uint32_t room_dict = (uint32_t)(in.dict_end - cand);
-                uint32_t lim = min(room_dict, (uint32_t)(mlimit - ip));         // limit - ip
-                mcode = warp_common_prefix(src + ip + 4, cand + 4, lim - 4);
-                if (4 + mcode == lim) {
-                    int at = ip + (int)lim;
-                    mcode += warp_common_prefix(src + at, src, (uint32_t)(mlimit - at));
-                }
+                uint32_t cap = (uint32_t)(mlimit - mip);
+                if (in_dict) cap = min(cap, (uint32_t)(in.dict_end - cand));
+                uint32_t L = 4 + warp_common_prefix(src + mip + 4, cand + 4, cap - 4);
+                if (in_dict && L == cap && mip + (int)L < mlimit)
+                    L += warp_common_prefix(src + mip + L, src, (uint32_t)(mlimit - (mip + (int)L)));
+                midx = (S + (uint32_t)mpos) - midx;     // from here on: the offset
+                mpos = mip; mlen = L;
+                out.push((uint32_t)anchor, (uint32_t)(mpos - anchor), mlen - 4, midx, in.block);
             } else {
-                mcode = warp_common_prefix(src + ip + 4, cand + 4, (uint32_t)(mlimit - (ip + 4)));
+                out.push((uint32_t)anchor, 0u, mlen - 4, (S + (uint32_t)mpos) - midx, in.block);
             }
-            // limitedOutput guards, :1024-1027 and :1097-1121
-            if (op + 1 + lit + (2 + 1 + kLastLiterals) + lit / 255 > in.cap) return 0;
-            {
-                uint8_t* tok = dst + op;
-                long long o = op + 1;
-                if (lit >= 15) { uint32_t rest = lit - 15, ne = rest / 255 + 1; emit_len_ext(dst + o, rest, ne); o += ne; }
-                warp_copy_ro(dst + o, src + anchor, lit); o += lit;
-                if (lane == 0) { dst[o] = (uint8_t)dist; dst[o + 1] = (uint8_t)(dist >> 8); }   // :1068
-                o += 2;
-                if (o + (1 + kLastLiterals) + (mcode + 240) / 255 > in.cap) return 0;
-                if (mcode >= 15) { uint32_t rest = mcode - 15, ne = rest / 255 + 1; emit_len_ext(dst + o, rest, ne); o += ne; }
-                if (lane == 0) *tok = (uint8_t)((min(lit, 15u) << 4) | min(mcode, 15u));
-                op = o;
-            }
-            ip += 4 + (int)mcode;
+            ip = mpos + (int)mlen;
             anchor = ip;
-            if (ip >= mfl) break;                                                            // :1143
-            if (lane == 0) { uint2 v = ldg_5bytes(src + ip - 2); table[hash5(v.x, v.y)] = S + (uint32_t)(ip - 2); }   // :1146
-            __syncwarp();
-            run_start = ip + 1;      // re-test at ip is probe -1 of the next run (:1159-1200)
-            retest = true;
+            if (ip >= mfl) break;                                                                    // :1143
+            after_match = true;
         }
     }
-    {   // last literals, :1204-1231
-        uint32_t run = (uint32_t)(n - anchor);
-        if (op + run + 1 + ((run + 255 - 15) / 255) > in.cap) return 0;
-        long long o = op + 1;
-        if (run >= 15) { uint32_t rest = run - 15, ne = rest / 255 + 1; emit_len_ext(dst + o, rest, ne); o += ne; }
-        if (lane == 0) dst[op] = (uint8_t)(min(run, 15u) << 4);
-        warp_copy_ro(dst + o, src + anchor, run); o += run;
-        op = o;
-    }
-    return (int)op;
+    // last literals, :1204-1231
+    out.push((uint32_t)anchor, (uint32_t)(n - anchor), 0u, 0u, in.block);
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-compress_kernel(CompressArgs a)
+__device__ void finder_main(const CompressArgs& a, uint32_t* table, Queue* q)
 {
-    extern __shared__ uint32_t smem_tables[];
     const uint32_t lane = lane_id();
-    const uint32_t warp = threadIdx.x >> 5;
-    uint32_t* table = smem_tables + warp * kHashEntries;
     uint32_t* counter = &a.scratch->work_counter[0];
     const int accel = a.accel < 1 ? 1 : (a.accel > kAccelMax ? kAccelMax : a.accel);   // :1577-1578
+    Producer out{q, 0, 0};
+    long long off0; int step0;
+    probe_schedule(lane, accel, off0, step0);           // first window of every search run
 
     for (;;) {
         int s = 0;
@@ -251,11 +339,7 @@ compress_kernel(CompressArgs a)
         for (int b = b0; b < b1; b++) {
             const uint8_t* src = a.src + a.src_off[b];
             const int n = a.src_len[b];
-            uint8_t* slot = a.dst + a.dst_off[b];
-            int r = 0;
             if (n >= 0 && n <= kMaxInput) {                                                  // :1262
-                const int bound = n + n / 255 + 16;
-                const int cap = a.dst_cap ? (a.dst_cap[b] - a.header) : bound;
                 if (offset + (uint32_t)n > 0x80000000u) {                                    // LZ4_renormDictT, :1545-1562
                     uint32_t delta = offset - 65536u;
                     for (int i = lane; i < kHashEntries; i += 32) { uint32_t v = table[i]; table[i] = v < delta ? 0u : v - delta; }
@@ -264,21 +348,15 @@ compress_kernel(CompressArgs a)
                     __syncwarp();
                 }
                 if (dict_len >= 1 && dict_len <= 3) dict_len = 0;                            // :1581-1587
-                if (n == 0) {                                                                // :1263-1273
-                    if (cap >= 1) { if (lane == 0) slot[a.header] = 0; r = 1; }
-                } else if (cap > 0) {
-                    BlockIn in{src, n, dict_end, dict_len, offset, slot + a.header, cap, accel};
-                    offset += (uint32_t)n;                                                   // :918
-                    r = encode_block(in, table);
-                    __syncwarp();
-                }
+                BlockIn in{src, n, dict_end, dict_len, offset, accel, b};
+                if (n > 0) offset += (uint32_t)n;                                            // :918 (n == 0 never reaches it, :1263-1273)
+                find_block(in, table, out, (uint32_t)off0, (uint32_t)step0);
+                __syncwarp();
                 dict_end = src + n; dict_len = (uint32_t)n;                                  // :1633-1634
                 last_src = src; last_n = n;
-            }
-            if (lane == 0) {
-                a.out_len[b] = r;
-                if (a.header >= 4) { uint32_t v = (uint32_t)r; for (int k = 0; k < 4; k++) slot[k] = (uint8_t)(v >> (8 * k)); }       // LZ4.hs:262
-                if (a.header == 8) { uint32_t v = (uint32_t)n; for (int k = 0; k < 4; k++) slot[4 + k] = (uint8_t)(v >> (8 * k)); }   // LZ4.hs:261
+                out.flush(b, kEndBlock);
+            } else {
+                out.flush(b, kEndBlock | (1 << 28));      // unsupported size: the emitter reports 0
             }
         }
         if (st) {   // persist the stream (what the reference keeps in LZ4_stream_t + the live previous array)
@@ -295,6 +373,116 @@ compress_kernel(CompressArgs a)
         }
         __syncwarp();
     }
+    out.flush(-1, kTerminate);
+}
+
+// encoded length-extension byte count for a nibble value v (0 if v < 15)
+__device__ __forceinline__ uint32_t ext_bytes(uint32_t v) { return v >= 15 ? (v - 15) / 255 + 1 : 0; }
+__device__ __forceinline__ void write_ext(uint8_t* p, uint32_t v)
+{   // v >= 15
+    uint32_t rest = v - 15;
+    while (rest >= 255) { *p++ = 255; rest -= 255; }
+    *p = (uint8_t)rest;
+}
+
+__device__ void emitter_main(const CompressArgs& a, Queue* q)
+{
+    const uint32_t lane = lane_id();
+    uint32_t batch = 0;
+    long long op = 0;               // bytes of the current block emitted so far
+    bool failed = false;
+    for (;;) {
+        const uint32_t b = batch & 1, t = batch >> 1;
+        mbar_wait(&q->full[b], t & 1);
+        const int cnt_flags = q->count[b];
+        const int blk = q->block[b];
+        const int cnt = cnt_flags & 0xFFFF;
+        if (cnt_flags & kTerminate) break;
+        const uint8_t* src = nullptr; uint8_t* dst = nullptr; long long cap = 0;
+        if (blk >= 0) {
+            src = a.src + a.src_off[blk];
+            const int n = a.src_len[blk];
+            dst = a.dst + a.dst_off[blk] + a.header;
+            cap = a.dst_cap ? (long long)a.dst_cap[blk] - a.header : (long long)n + n / 255 + 16;
+        }
+        if (cnt_flags & (1 << 28)) failed = true;
+        uint4 d = make_uint4(0, 0, 0, 0);
+        if ((int)lane < cnt) d = q->desc[b][lane];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q->empty[b]);       // descriptors are in registers: hand the buffer back
+        batch++;
+
+        const uint32_t lit = d.y, mcode = d.z, off = d.w;
+        const bool is_seq = (int)lane < cnt;
+        const uint32_t le = ext_bytes(lit);
+        uint32_t size = 0;
+        if (is_seq) size = 1 + le + lit + (off ? 2 + ext_bytes(mcode) : 0);
+        // inclusive warp scan of sizes (64-bit safe: one block is < 2 GiB + bound)
+        uint32_t incl = size;
+        #pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t v = __shfl_up_sync(kFull, incl, dlt); if ((int)lane >= dlt) incl += v; }
+        const long long start = op + (long long)(incl - size);
+        // limitedOutput guards of the reference, evaluated at this sequence's output position
+        bool bad = false;
+        if (is_seq) {
+            if (off) {
+                bad = (start + 1 + lit + (2 + 1 + kLastLiterals) + lit / 255 > cap)                       // :1024-1027
+                   || (start + 1 + le + lit + 2 + (1 + kLastLiterals) + (mcode + 240) / 255 > cap);      // :1097-1121
+            } else {
+                bad = (start + lit + 1 + ((lit + 255 - 15) / 255) > cap);                                // :1207-1217
+            }
+        }
+        if (__ballot_sync(kFull, bad)) failed = true;
+        if (!failed && is_seq) {
+            uint8_t* p = dst + start;
+            *p++ = (uint8_t)((min(lit, 15u) << 4) | (off ? min(mcode, 15u) : 0u));
+            if (le) { write_ext(p, lit); p += le; }
+            if (lit <= 16) { const uint8_t* s = src + d.x; for (uint32_t i = 0; i < lit; i++) p[i] = __ldg(s + i); }
+            p += lit;
+            if (off) {
+                p[0] = (uint8_t)off; p[1] = (uint8_t)(off >> 8);                                         // :1068
+                if (mcode >= 15) write_ext(p + 2, mcode);                                                // :1123-1135
+            }
+        }
+        // long literal runs: cooperative copies, one run at a time
+        uint32_t longs = __ballot_sync(kFull, !failed && is_seq && lit > 16);
+        while (longs) {
+            const int l = __ffs(longs) - 1; longs &= longs - 1;
+            const uint32_t l_pos = __shfl_sync(kFull, d.x, l), l_len = __shfl_sync(kFull, lit, l);
+            const uint32_t l_le = __shfl_sync(kFull, le, l);
+            const uint32_t l_rel = __shfl_sync(kFull, incl - size, l);
+            warp_copy_ro(dst + op + l_rel + 1 + l_le, src + l_pos, l_len);
+        }
+        op += (long long)__shfl_sync(kFull, incl, 31);
+        if (cnt_flags & kEndBlock) {
+            const int r = failed ? 0 : (int)op;
+            if (lane == 0 && blk >= 0) {
+                uint8_t* slot = a.dst + a.dst_off[blk];
+                a.out_len[blk] = r;
+                if (a.header >= 4) { uint32_t v = (uint32_t)r; for (int k = 0; k < 4; k++) slot[k] = (uint8_t)(v >> (8 * k)); }                 // LZ4.hs:262
+                if (a.header == 8) { uint32_t v = (uint32_t)a.src_len[blk]; for (int k = 0; k < 4; k++) slot[4 + k] = (uint8_t)(v >> (8 * k)); }   // LZ4.hs:261
+            }
+            op = 0; failed = false;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPairs * 64)
+compress_kernel(CompressArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t* tables = reinterpret_cast<uint32_t*>(smem_raw);
+    Queue* queues = reinterpret_cast<Queue*>(smem_raw + kPairs * kHashEntries * sizeof(uint32_t));
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t pair = warp & (kPairs - 1);
+    if (threadIdx.x < kPairs) {
+        Queue* q = &queues[threadIdx.x];
+        mbar_init(&q->full[0], 1); mbar_init(&q->full[1], 1);
+        mbar_init(&q->empty[0], 1); mbar_init(&q->empty[1], 1);
+    }
+    __syncthreads();
+    if (warp < kPairs) finder_main(a, tables + pair * kHashEntries, &queues[pair]);
+    else emitter_main(a, &queues[pair]);
     // last CTA out resets the work counter so the scratch stays zeroed for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -305,28 +493,26 @@ compress_kernel(CompressArgs a)
 
 }  // namespace
 
-constexpr int kCompressWarps = 4;
-
 cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
 {
     static int sm_counts[64] = {0};     // per device: SM count, 0 = kernel not configured there yet
-    const size_t smem = kCompressWarps * kHashEntries * sizeof(uint32_t);
+    const size_t smem = kPairs * kHashEntries * sizeof(uint32_t) + kPairs * sizeof(Queue);
     int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!sm_counts[dev]) {
         int n = 0;
         e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(compress_kernel<kCompressWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         sm_counts[dev] = n;
     }
     const int sm_count = sm_counts[dev];
     if (a.n_streams <= 0) return cudaSuccess;
-    int ctas_per_sm = 3;                         // 3 x 64 KiB of tables per SM
-    int max_ctas = sm_count * ctas_per_sm;
-    int want = (a.n_streams + kCompressWarps - 1) / kCompressWarps;
-    int grid = want < max_ctas ? want : max_ctas;
-    compress_kernel<kCompressWarps><<<grid, kCompressWarps * 32, smem, stream>>>(a);
+    const int ctas_per_sm = 3;                   // 3 x (64 KiB of tables + queues) per SM
+    const int max_ctas = sm_count * ctas_per_sm;
+    const int want = (a.n_streams + kPairs - 1) / kPairs;
+    const int grid = want < max_ctas ? want : max_ctas;
+    compress_kernel<<<grid, kPairs * 64, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
