@@ -2,6 +2,8 @@
 // the batched host/device entry points, re-framing and the legacy LZ4_* aliases.
 // There is no CPU codec in this library: every compress/decompress call runs the
 // sm_100a kernels, and fails with B200LZ4_E_CUDA when no such device is usable.
+#include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -63,13 +65,20 @@ struct PinBuf {
 
 }  // namespace
 
+constexpr int kMaxChunks = 6;           // pipeline depth of the host batch calls (H2D + D2H + chunk streams must fit the
+                                        // 8 hardware queues of the default CUDA_DEVICE_MAX_CONNECTIONS, else chunks serialize)
+constexpr int kKernelStreams = kMaxChunks;   // one stream per chunk: chunk kernels must be able to overlap
+
 struct b200lz4_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
-    Scratch* scratch = nullptr;
+    cudaStream_t stream = nullptr;                  // H2D + bookkeeping
+    cudaStream_t kstream[kKernelStreams] = {};      // chunk kernels (run concurrently)
+    cudaStream_t dstream = nullptr;                 // D2H
+    Scratch* scratch = nullptr;                     // kMaxChunks records: one work counter per in-flight kernel
     DevBuf d_src, d_slots, d_out, d_desc;
     PinBuf h_desc;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_k0 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
     int64_t launches = 0;
 };
@@ -133,6 +142,46 @@ int cstream_reserve(b200lz4_cstream* s, uint32_t need)
     return 0;
 }
 
+int sync_all(b200lz4_ctx* c)
+{
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto& k : c->kstream) CU(cudaStreamSynchronize(k));
+    CU(cudaStreamSynchronize(c->dstream));
+    return 0;
+}
+
+// ---- pipeline planning ------------------------------------------------------
+// A host batch is cut into up to kMaxChunks chunks of whole streams (independent mode: whole
+// blocks).  Chunk k's H2D copy, its kernels and its D2H copy run on three different CUDA
+// streams, so that transfers in both directions overlap the kernels of neighbouring chunks;
+// the chunk kernels themselves run concurrently on kKernelStreams streams because a codec
+// kernel is bound by per-block latency, not by the number of blocks it is given.
+struct Chunk { int b0, b1, s0, s1; int64_t lo, hi; };
+
+int plan_chunks(const int64_t* off, const int32_t* len, int n, const int32_t* first, int ns, Chunk* out)
+{
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) total += len[i];
+    const int64_t target = std::max<int64_t>(int64_t(24) << 20, (total + kMaxChunks - 1) / kMaxChunks);
+    int k = 0, unit = 0;
+    const int units = first ? ns : n;
+    while (unit < units) {
+        Chunk c; c.s0 = unit; c.b0 = first ? first[unit] : unit;
+        int64_t bytes = 0;
+        while (unit < units && (bytes < target || k == kMaxChunks - 1)) {
+            const int u0 = first ? first[unit] : unit, u1 = first ? first[unit + 1] : unit + 1;
+            for (int i = u0; i < u1; i++) bytes += len[i];
+            unit++;
+        }
+        c.s1 = unit; c.b1 = first ? first[unit] : unit;
+        c.lo = INT64_MAX; c.hi = 0;
+        for (int i = c.b0; i < c.b1; i++) { c.lo = std::min(c.lo, off[i]); c.hi = std::max(c.hi, off[i] + (int64_t)len[i]); }
+        if (c.lo > c.hi) c.lo = c.hi = 0;
+        out[k++] = c;
+    }
+    return k;
+}
+
 int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
                   const int64_t* src_off, const int32_t* src_len, int n,
                   const int32_t* stream_first, int n_streams, b200lz4_cstream* const* streams,
@@ -161,6 +210,8 @@ int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
             }
         }
     }
+    Chunk chunks[kMaxChunks];
+    const int nchunks = plan_chunks(src_off, src_len, n, stream_first, ns, chunks);
 
     // descriptor block
     Carver cv;
@@ -172,7 +223,7 @@ int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     const size_t o_states = cv.take(sizeof(void*) * ns);
     const size_t o_upload_end = cv.off;
     const size_t o_out_len = cv.take(sizeof(int32_t) * n);
-    const size_t o_out_off = cv.take(sizeof(int64_t) * (n + 1));
+    const size_t o_out_off = cv.take(sizeof(int64_t) * (n + nchunks));
     const size_t desc_bytes = cv.off;
     if ((rc = c->h_desc.ensure(desc_bytes))) return rc;
     if ((rc = c->d_desc.ensure(desc_bytes))) return rc;
@@ -197,45 +248,77 @@ int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     if ((rc = c->d_slots.ensure((size_t)slots_total + 64))) return rc;
     if ((rc = c->d_out.ensure((size_t)slots_total + 64))) return rc;
 
+    const uint8_t* hsrc = static_cast<const uint8_t*>(src);
+    uint8_t* d_src = static_cast<uint8_t*>(c->d_src.p);
+    uint8_t* d_slots = static_cast<uint8_t*>(c->d_slots.p);
+    uint8_t* d_out = static_cast<uint8_t*>(c->d_out.p);
+    int64_t* d_out_off = reinterpret_cast<int64_t*>(dd + o_out_off);
+    int32_t* d_out_len = reinterpret_cast<int32_t*>(dd + o_out_len);
+
     cudaStream_t st = c->stream;
     CU(cudaEventRecord(c->ev[0], st));
-    if (src_bytes) CU(cudaMemcpyAsync(c->d_src.p, src, (size_t)src_bytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dd, hd, o_upload_end, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < nchunks; k++) {
+        const Chunk& ch = chunks[k];
+        if (ch.hi > ch.lo) CU(cudaMemcpyAsync(d_src + ch.lo, hsrc + ch.lo, (size_t)(ch.hi - ch.lo), cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->ev_h2d[k], st));
+        cudaStream_t ks = c->kstream[k % kKernelStreams];
+        CU(cudaStreamWaitEvent(ks, c->ev_h2d[k], 0));
+        if (k == 0) CU(cudaEventRecord(c->ev_k0, ks));
+        CompressArgs a{};
+        a.src = d_src;
+        a.src_off = reinterpret_cast<const int64_t*>(dd + o_src_off);
+        a.src_len = reinterpret_cast<const int32_t*>(dd + o_src_len);
+        a.n_blocks = n;
+        a.first_block = ch.b0;
+        a.stream_first = stream_first ? reinterpret_cast<const int32_t*>(dd + o_first) + ch.s0 : nullptr;
+        a.n_streams = ch.s1 - ch.s0;
+        a.states = streams ? reinterpret_cast<void* const*>(dd + o_states) + ch.s0 : nullptr;
+        a.dst = d_slots;
+        a.dst_off = reinterpret_cast<const int64_t*>(dd + o_slot_off);
+        a.dst_cap = block_cap ? reinterpret_cast<const int32_t*>(dd + o_cap) : nullptr;
+        a.out_len = d_out_len;
+        a.accel = accel; a.header = header; a.scratch = c->scratch + k;
+        CU(launch_compress(a, ks));
+        const int nk = ch.b1 - ch.b0;
+        CompactArgs g{d_slots, a.dst_off + ch.b0, d_out_len + ch.b0, nk, header, d_out + h_slot_off[ch.b0], d_out_off + ch.b0 + k};
+        CU(launch_compact(g, ks));
+        c->launches += kernel_launches_per_compress() + kernel_launches_per_compact();
+        CU(cudaMemcpyAsync(hd + o_out_len + sizeof(int32_t) * ch.b0, dd + o_out_len + sizeof(int32_t) * ch.b0,
+                           sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, ks));
+        CU(cudaMemcpyAsync(hd + o_out_off + sizeof(int64_t) * (ch.b0 + k), dd + o_out_off + sizeof(int64_t) * (ch.b0 + k),
+                           sizeof(int64_t) * (nk + 1), cudaMemcpyDeviceToHost, ks));
+        if (k == nchunks - 1) CU(cudaEventRecord(c->ev[2], ks));
+        CU(cudaEventRecord(c->ev_k[k], ks));
+    }
     CU(cudaEventRecord(c->ev[1], st));
 
-    CompressArgs a{};
-    a.src = static_cast<const uint8_t*>(c->d_src.p);
-    a.src_off = reinterpret_cast<const int64_t*>(dd + o_src_off);
-    a.src_len = reinterpret_cast<const int32_t*>(dd + o_src_len);
-    a.n_blocks = n;
-    a.stream_first = stream_first ? reinterpret_cast<const int32_t*>(dd + o_first) : nullptr;
-    a.n_streams = ns;
-    a.states = streams ? reinterpret_cast<void* const*>(dd + o_states) : nullptr;
-    a.dst = static_cast<uint8_t*>(c->d_slots.p);
-    a.dst_off = reinterpret_cast<const int64_t*>(dd + o_slot_off);
-    a.dst_cap = block_cap ? reinterpret_cast<const int32_t*>(dd + o_cap) : nullptr;
-    a.out_len = reinterpret_cast<int32_t*>(dd + o_out_len);
-    a.accel = accel; a.header = header; a.scratch = c->scratch;
-    CU(launch_compress(a, st));
-    CompactArgs g{a.dst, a.dst_off, a.out_len, n, header, static_cast<uint8_t*>(c->d_out.p),
-                  reinterpret_cast<int64_t*>(dd + o_out_off)};
-    CU(launch_compact(g, st));
-    c->launches += kernel_launches_per_compress() + kernel_launches_per_compact();
-    CU(cudaEventRecord(c->ev[2], st));
-    CU(cudaMemcpyAsync(hd + o_out_len, dd + o_out_len, desc_bytes - o_out_len, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    // drain: as each chunk's sizes arrive, send its compacted bytes home
     const int32_t* h_out_len = reinterpret_cast<const int32_t*>(hd + o_out_len);
     const int64_t* h_out_off = reinterpret_cast<const int64_t*>(hd + o_out_off);
-    const int64_t total = h_out_off[n];
+    int64_t base = 0;
+    int result = 0;
+    CU(cudaEventRecord(c->ev_d0, c->dstream));
+    for (int k = 0; k < nchunks; k++) {
+        const Chunk& ch = chunks[k];
+        CU(cudaEventSynchronize(c->ev_k[k]));
+        const int nk = ch.b1 - ch.b0;
+        const int64_t* off_k = h_out_off + ch.b0 + k;
+        const int64_t total_k = off_k[nk];
+        for (int i = 0; i < nk; i++) dst_off[ch.b0 + i] = base + off_k[i];
+        if (base + total_k > dst_cap) { result = fail(B200LZ4_E_NOMEM, "dst_cap too small"); break; }
+        if (total_k) CU(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + base, d_out + h_slot_off[ch.b0], (size_t)total_k,
+                                        cudaMemcpyDeviceToHost, c->dstream));
+        base += total_k;
+    }
+    dst_off[n] = base;
+    CU(cudaEventRecord(c->ev_d1, c->dstream));
+    if ((rc = sync_all(c))) return rc;
+    if (result) return result;
     memcpy(out_len, h_out_len, sizeof(int32_t) * n);
-    memcpy(dst_off, h_out_off, sizeof(int64_t) * (n + 1));
-    if (total > dst_cap) return fail(B200LZ4_E_NOMEM, "dst_cap too small: need " + std::to_string(total));
-    if (total) CU(cudaMemcpyAsync(dst, c->d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(c->ev[3], st));
-    CU(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&c->t_kernel, c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&c->t_d2h, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->t_kernel, c->ev_k0, c->ev[2]);
+    cudaEventElapsedTime(&c->t_d2h, c->ev_d0, c->ev_d1);
     if (streams) for (int s = 0; s < n_streams; s++)
         if (stream_first[s + 1] > stream_first[s]) streams[s]->last_len = (uint32_t)src_len[stream_first[s + 1] - 1];
     for (int i = 0; i < n; i++) if (out_len[i] <= 0) return fail(B200LZ4_E_BLOCK, "block " + std::to_string(i) + " failed to compress");
@@ -265,6 +348,8 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     const int ns = stream_first ? n_streams : n;
     if (streams) for (int s = 0; s < n_streams; s++)
         if (!streams[s] || streams[s]->ctx != c) return fail(B200LZ4_E_ARG, "stream handle belongs to another ctx");
+    Chunk chunks[kMaxChunks];
+    const int nchunks = plan_chunks(src_off, src_len, n, stream_first, ns, chunks);
 
     Carver cv;
     const size_t o_src_off = cv.take(sizeof(int64_t) * n);
@@ -275,7 +360,7 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     const size_t o_states = cv.take(sizeof(void*) * ns);
     const size_t o_upload_end = cv.off;
     const size_t o_out_len = cv.take(sizeof(int32_t) * n);
-    const size_t o_out_off = cv.take(sizeof(int64_t) * (n + 1));
+    const size_t o_out_off = cv.take(sizeof(int64_t) * (n + nchunks));
     const size_t desc_bytes = cv.off;
     if ((rc = c->h_desc.ensure(desc_bytes))) return rc;
     if ((rc = c->d_desc.ensure(desc_bytes))) return rc;
@@ -304,53 +389,86 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     if ((rc = c->d_src.ensure((size_t)src_bytes + 64))) return rc;
     if ((rc = c->d_slots.ensure((size_t)slots_total + 64))) return rc;
     if (!contiguous && (rc = c->d_out.ensure((size_t)slots_total + 64))) return rc;
+    uint8_t* d_src = static_cast<uint8_t*>(c->d_src.p);
+    uint8_t* d_slots = static_cast<uint8_t*>(c->d_slots.p);
+    uint8_t* d_out = static_cast<uint8_t*>(c->d_out.p);
+    int64_t* d_out_off = reinterpret_cast<int64_t*>(dd + o_out_off);
+    int32_t* d_out_len = reinterpret_cast<int32_t*>(dd + o_out_len);
 
     cudaStream_t st = c->stream;
     CU(cudaEventRecord(c->ev[0], st));
-    if (src_bytes) CU(cudaMemcpyAsync(c->d_src.p, src, (size_t)src_bytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dd, hd, o_upload_end, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->ev_d0, c->dstream));
+    for (int k = 0; k < nchunks; k++) {
+        const Chunk& ch = chunks[k];
+        if (ch.hi > ch.lo) CU(cudaMemcpyAsync(d_src + ch.lo, hsrc + ch.lo, (size_t)(ch.hi - ch.lo), cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->ev_h2d[k], st));
+        cudaStream_t ks = c->kstream[k % kKernelStreams];
+        CU(cudaStreamWaitEvent(ks, c->ev_h2d[k], 0));
+        if (k == 0) CU(cudaEventRecord(c->ev_k0, ks));
+        DecompressArgs a{};
+        a.src = d_src;
+        a.src_off = reinterpret_cast<const int64_t*>(dd + o_src_off);
+        a.src_len = reinterpret_cast<const int32_t*>(dd + o_src_len);
+        a.n_blocks = n;
+        a.first_block = ch.b0;
+        a.stream_first = stream_first ? reinterpret_cast<const int32_t*>(dd + o_first) + ch.s0 : nullptr;
+        a.n_streams = ch.s1 - ch.s0;
+        a.states = streams ? reinterpret_cast<void* const*>(dd + o_states) + ch.s0 : nullptr;
+        a.dst = d_slots;
+        a.dst_off = reinterpret_cast<const int64_t*>(dd + o_slot_off);
+        a.dst_cap = reinterpret_cast<const int32_t*>(dd + o_cap);
+        a.out_len = d_out_len;
+        a.header = header; a.max_block = max_block; a.scratch = c->scratch + k;
+        CU(launch_decompress(a, ks));
+        c->launches += kernel_launches_per_decompress();
+        const int nk = ch.b1 - ch.b0;
+        if (!contiguous) {
+            CompactArgs g{d_slots, a.dst_off + ch.b0, d_out_len + ch.b0, nk, 0, d_out + h_slot_off[ch.b0], d_out_off + ch.b0 + k};
+            CU(launch_compact(g, ks));
+            c->launches += kernel_launches_per_compact();
+            CU(cudaMemcpyAsync(hd + o_out_off + sizeof(int64_t) * (ch.b0 + k), dd + o_out_off + sizeof(int64_t) * (ch.b0 + k),
+                               sizeof(int64_t) * (nk + 1), cudaMemcpyDeviceToHost, ks));
+        }
+        CU(cudaMemcpyAsync(hd + o_out_len + sizeof(int32_t) * ch.b0, dd + o_out_len + sizeof(int32_t) * ch.b0,
+                           sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, ks));
+        if (k == nchunks - 1) CU(cudaEventRecord(c->ev[2], ks));
+        CU(cudaEventRecord(c->ev_k[k], ks));
+        if (contiguous) {   // sizes are known from the headers: the D2H copy can be queued right away
+            const int64_t lo = h_slot_off[ch.b0];
+            const int64_t hi = (ch.b1 < n) ? h_slot_off[ch.b1] : slots_total;
+            CU(cudaStreamWaitEvent(c->dstream, c->ev_k[k], 0));
+            if (hi > lo) CU(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + lo, d_slots + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, c->dstream));
+        }
+    }
     CU(cudaEventRecord(c->ev[1], st));
-
-    DecompressArgs a{};
-    a.src = static_cast<const uint8_t*>(c->d_src.p);
-    a.src_off = reinterpret_cast<const int64_t*>(dd + o_src_off);
-    a.src_len = reinterpret_cast<const int32_t*>(dd + o_src_len);
-    a.n_blocks = n;
-    a.stream_first = stream_first ? reinterpret_cast<const int32_t*>(dd + o_first) : nullptr;
-    a.n_streams = ns;
-    a.states = streams ? reinterpret_cast<void* const*>(dd + o_states) : nullptr;
-    a.dst = static_cast<uint8_t*>(c->d_slots.p);
-    a.dst_off = reinterpret_cast<const int64_t*>(dd + o_slot_off);
-    a.dst_cap = reinterpret_cast<const int32_t*>(dd + o_cap);
-    a.out_len = reinterpret_cast<int32_t*>(dd + o_out_len);
-    a.header = header; a.max_block = max_block; a.scratch = c->scratch;
-    CU(launch_decompress(a, st));
-    c->launches += kernel_launches_per_decompress();
-    const uint8_t* d_result = a.dst;
-    if (!contiguous) {
-        CompactArgs g{a.dst, a.dst_off, a.out_len, n, 0, static_cast<uint8_t*>(c->d_out.p),
-                      reinterpret_cast<int64_t*>(dd + o_out_off)};
-        CU(launch_compact(g, st));
-        c->launches += kernel_launches_per_compact();
-        d_result = g.out;
+    int result = 0;
+    if (contiguous) {
+        memcpy(dst_off, h_slot_off, sizeof(int64_t) * n); dst_off[n] = slots_total;
+    } else {
+        const int64_t* h_out_off = reinterpret_cast<const int64_t*>(hd + o_out_off);
+        int64_t base = 0;
+        for (int k = 0; k < nchunks; k++) {
+            const Chunk& ch = chunks[k];
+            CU(cudaEventSynchronize(c->ev_k[k]));
+            const int nk = ch.b1 - ch.b0;
+            const int64_t* off_k = h_out_off + ch.b0 + k;
+            const int64_t total_k = off_k[nk];
+            for (int i = 0; i < nk; i++) dst_off[ch.b0 + i] = base + off_k[i];
+            if (base + total_k > dst_cap) { result = fail(B200LZ4_E_NOMEM, "dst_cap too small"); break; }
+            if (total_k) CU(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + base, d_out + h_slot_off[ch.b0], (size_t)total_k,
+                                            cudaMemcpyDeviceToHost, c->dstream));
+            base += total_k;
+        }
+        dst_off[n] = base;
     }
-    CU(cudaEventRecord(c->ev[2], st));
-    CU(cudaMemcpyAsync(hd + o_out_len, dd + o_out_len, desc_bytes - o_out_len, cudaMemcpyDeviceToHost, st));
-    int64_t total = slots_total;
-    if (!contiguous) {
-        CU(cudaStreamSynchronize(st));
-        total = reinterpret_cast<const int64_t*>(hd + o_out_off)[n];
-        if (total > dst_cap) return fail(B200LZ4_E_NOMEM, "dst_cap too small: need " + std::to_string(total));
-    }
-    if (total) CU(cudaMemcpyAsync(dst, d_result, (size_t)total, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(c->ev[3], st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaEventRecord(c->ev_d1, c->dstream));
+    if ((rc = sync_all(c))) return rc;
+    if (result) return result;
     cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&c->t_kernel, c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&c->t_d2h, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->t_kernel, c->ev_k0, c->ev[2]);
+    cudaEventElapsedTime(&c->t_d2h, c->ev_d0, c->ev_d1);
     memcpy(out_len, hd + o_out_len, sizeof(int32_t) * n);
-    if (contiguous) { memcpy(dst_off, h_slot_off, sizeof(int64_t) * n); dst_off[n] = slots_total; }
-    else memcpy(dst_off, hd + o_out_off, sizeof(int64_t) * (n + 1));
     for (int i = 0; i < n; i++) if (out_len[i] < 0) return fail(B200LZ4_E_BLOCK, "block " + std::to_string(i) + " failed to decompress");
     return 0;
 }
@@ -393,9 +511,18 @@ int b200lz4_ctx_create(int device, b200lz4_ctx** out)
     if (!c) return fail(B200LZ4_E_NOMEM, "out of host memory");
     c->device = device;
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(&c->scratch, sizeof(Scratch));
-    if (e2 == cudaSuccess) e2 = cudaMemset(c->scratch, 0, sizeof(Scratch));
+    for (int i = 0; i < kKernelStreams && e2 == cudaSuccess; i++) e2 = cudaStreamCreateWithFlags(&c->kstream[i], cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->dstream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&c->scratch, sizeof(Scratch) * kMaxChunks);
+    if (e2 == cudaSuccess) e2 = cudaMemset(c->scratch, 0, sizeof(Scratch) * kMaxChunks);
     for (int i = 0; i < 4 && e2 == cudaSuccess; i++) e2 = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < kMaxChunks && e2 == cudaSuccess; i++) {
+        e2 = cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming);
+    }
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev_k0);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev_d0);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev_d1);
     if (e2 != cudaSuccess) { b200lz4_ctx_destroy(c); return fail_cuda(e2, "ctx_create"); }
     *out = c;
     return 0;
@@ -405,10 +532,17 @@ void b200lz4_ctx_destroy(b200lz4_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaDeviceSynchronize();
     c->d_src.release(); c->d_slots.release(); c->d_out.release(); c->d_desc.release(); c->h_desc.release();
     if (c->scratch) cudaFree(c->scratch);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_h2d) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_k) if (e) cudaEventDestroy(e);
+    if (c->ev_k0) cudaEventDestroy(c->ev_k0);
+    if (c->ev_d0) cudaEventDestroy(c->ev_d0);
+    if (c->ev_d1) cudaEventDestroy(c->ev_d1);
+    for (auto& k : c->kstream) if (k) cudaStreamDestroy(k);
+    if (c->dstream) cudaStreamDestroy(c->dstream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

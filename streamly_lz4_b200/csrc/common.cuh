@@ -74,11 +74,26 @@ __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p)
 
 // LZ4_hash5 on a little-endian 64-bit target (cbits/lz4.c:706-716): only the low
 // 5 bytes of the 8 the reference reads reach the result.
+// ((five << 24) * P) >> 52 == bits 28..39 of (five * P) mod 2^40, evaluated with 32-bit
+// multiplies: P = 0xCF_1BBCDCBB, five = lo4 + b4 * 2^32.
 __device__ __forceinline__ uint32_t hash5(uint32_t lo4, uint32_t b4)
 {
-    unsigned long long five = (unsigned long long)lo4 | ((unsigned long long)b4 << 32);
-    return (uint32_t)(((five << 24) * 889523592379ULL) >> 52);
+    constexpr uint32_t kPl = 0x1BBCDCBBu, kPh = 0xCFu;
+    const uint32_t tl = lo4 * kPl;
+    const uint32_t th = __umulhi(lo4, kPl) + lo4 * kPh + b4 * kPl;
+    return (tl >> 28) | ((th & 0xFFu) << 4);
 }
+
+// ---- cache-policy helpers ---------------------------------------------------
+// Streaming reads/writes of the emitter and of far probe lanes must not evict the few KiB of
+// L1 that serve the match finder's current lines.
+__device__ __forceinline__ uint32_t ldg_na_u32(const uint32_t* p)
+{ uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldg_na_u8(const uint8_t* p)
+{ uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint4 ldg_na_u128(const uint4* p)
+{ uint4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---- warp-cooperative copies ----------------------------------------------
 // dst/src arbitrary alignment, non-overlapping, src read-only for the kernel.
@@ -87,12 +102,12 @@ __device__ __forceinline__ void warp_copy_ro(uint8_t* __restrict__ dst, const ui
 {
     const uint32_t lane = lane_id();
     if (len < 96) {
-        for (uint32_t i = lane; i < len; i += 32) dst[i] = __ldg(src + i);
+        for (uint32_t i = lane; i < len; i += 32) dst[i] = (uint8_t)ldg_na_u8(src + i);
         return;
     }
     // head: bring dst to 16-byte alignment
     uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
-    if (lane < head) dst[lane] = __ldg(src + lane);
+    if (lane < head) dst[lane] = (uint8_t)ldg_na_u8(src + lane);
     dst += head; src += head; len -= head;
     const uint32_t nvec = len >> 4;
     uintptr_t sa = reinterpret_cast<uintptr_t>(src);
@@ -102,24 +117,24 @@ __device__ __forceinline__ void warp_copy_ro(uint8_t* __restrict__ dst, const ui
     if (sh == 0) {
         if ((sa & 15) == 0) {
             const uint4* sv = reinterpret_cast<const uint4*>(src);
-            for (uint32_t v = lane; v < nvec; v += 32) dv[v] = __ldg(sv + v);
+            for (uint32_t v = lane; v < nvec; v += 32) dv[v] = ldg_na_u128(sv + v);
         } else {
             for (uint32_t v = lane; v < nvec; v += 32) {
                 const uint32_t* q = sw + 4 * v;
-                dv[v] = make_uint4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+                dv[v] = make_uint4(ldg_na_u32(q), ldg_na_u32(q + 1), ldg_na_u32(q + 2), ldg_na_u32(q + 3));
             }
         }
     } else {
         for (uint32_t v = lane; v < nvec; v += 32) {
             const uint32_t* q = sw + 4 * v;
-            uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
+            uint32_t a = ldg_na_u32(q), b = ldg_na_u32(q + 1), c = ldg_na_u32(q + 2), d = ldg_na_u32(q + 3), e = ldg_na_u32(q + 4);
             dv[v] = make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh),
                                __funnelshift_r(c, d, sh), __funnelshift_r(d, e, sh));
         }
     }
     const uint32_t done = nvec << 4;
     const uint32_t tail = len - done;
-    if (lane < tail) dst[done + lane] = __ldg(src + done + lane);
+    if (lane < tail) dst[done + lane] = (uint8_t)ldg_na_u8(src + done + lane);
 }
 
 }  // namespace b200lz4

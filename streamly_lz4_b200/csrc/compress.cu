@@ -62,11 +62,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint: do not burn issue slots while idle
 }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes)
 { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
@@ -97,6 +97,34 @@ __device__ __forceinline__ uint32_t warp_common_prefix(const uint8_t* a, const u
         } else if (at < cap) {
             const uint32_t room = cap - at;
             while (nb < room && __ldg(a + at + nb) == __ldg(b + at + nb)) nb++;
+        }
+        const uint32_t sb = __ballot_sync(kFull, stop);
+        if (sb) {
+            const int l = __ffs(sb) - 1;
+            const uint32_t res = __shfl_sync(kFull, at + nb, l);
+            return res < cap ? res : cap;
+        }
+        base += 128;
+    }
+}
+
+// Number of equal bytes walking backwards from a[-1], b[-1], at most cap (the catch-up loop,
+// cbits/lz4.c:1019), 4 bytes per lane per round.
+__device__ __forceinline__ uint32_t warp_common_suffix(const uint8_t* a, const uint8_t* b, uint32_t cap)
+{
+    const uint32_t lane = lane_id();
+    uint32_t base = 0;
+    for (;;) {
+        const uint32_t at = base + lane * 4;        // this lane covers bytes [-(at+4), -at)
+        uint32_t nb = 0;
+        bool stop = true;
+        if (at + 4 <= cap) {
+            uint32_t x = ldg_u32_unaligned(a - at - 4) ^ ldg_u32_unaligned(b - at - 4);
+            nb = x ? ((uint32_t)__clz(x) >> 3) : 4u;
+            stop = (nb < 4);
+        } else if (at < cap) {
+            const uint32_t room = cap - at;
+            while (nb < room && __ldg(a - at - nb - 1) == __ldg(b - at - nb - 1)) nb++;
         }
         const uint32_t sb = __ballot_sync(kFull, stop);
         if (sb) {
@@ -164,6 +192,7 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, Producer& out,
 
     if (n >= kMinLength) {
         uint32_t pf_next = 0;                  // next input byte not yet requested into L2
+        uint32_t l1_line = 0xFFFFFFFFu;
         if (lane == 0) { uint2 v = ldg_5bytes(src); table[hash5(v.x, v.y)] = S; }   // :924
         __syncwarp();
         int ip = 1;                            // :925  (search runs start here)
@@ -180,6 +209,13 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, Producer& out,
                 pf_next += kPrefetchChunk;
             }
 
+            {   // pull the next two 128-byte lines into L1 ahead of the scalar path
+                const uint32_t line = (uint32_t)((reinterpret_cast<uintptr_t>(src) + (uint32_t)ip) >> 7);
+                if (line != l1_line) {
+                    l1_line = line;
+                    if (lane < 2 && ip + 128 * (int)(lane + 1) < n) prefetch_l1(src + ip + 128 * (lane + 1));
+                }
+            }
             int mpos; uint32_t midx; uint32_t mlen;     // match start, table index of its source, total length
             bool have = false;
             if (after_match) {
@@ -271,15 +307,7 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, Producer& out,
                 {
                     const uint32_t room_c = in_dict ? (in.dict_len - (S - midx)) : (midx - S);
                     const uint32_t maxback = min((uint32_t)(mip - anchor), room_c);
-                    uint32_t back = 0;
-                    while (back < maxback) {
-                        const uint32_t k = back + lane + 1;
-                        const bool eq = (k <= maxback) && (__ldg(src + mip - k) == __ldg(cand - k));
-                        const uint32_t b = __ballot_sync(kFull, eq);
-                        const uint32_t run = (b == kFull) ? 32u : (uint32_t)(__ffs(~b) - 1);
-                        back += run;
-                        if (run < 32) break;
-                    }
+                    const uint32_t back = maxback ? warp_common_suffix(src + mip, cand, maxback) : 0u;
                     mip -= (int)back; cand -= back;
                 }
                 uint32_t cap = (uint32_t)(mlimit - mip);
@@ -317,8 +345,8 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, Queue* q)
         if (lane == 0) s = (int)atomicAdd(counter, 1u);
         s = __shfl_sync(kFull, s, 0);
         if (s >= a.n_streams) break;
-        const int b0 = a.stream_first ? a.stream_first[s] : s;
-        const int b1 = a.stream_first ? a.stream_first[s + 1] : s + 1;
+        const int b0 = a.stream_first ? a.stream_first[s] : a.first_block + s;
+        const int b1 = a.stream_first ? a.stream_first[s + 1] : b0 + 1;
         CState* st = a.states ? reinterpret_cast<CState*>(a.states[s]) : nullptr;
 
         uint32_t offset = 0, dict_len = 0;
@@ -437,7 +465,7 @@ __device__ void emitter_main(const CompressArgs& a, Queue* q)
             uint8_t* p = dst + start;
             *p++ = (uint8_t)((min(lit, 15u) << 4) | (off ? min(mcode, 15u) : 0u));
             if (le) { write_ext(p, lit); p += le; }
-            if (lit <= 16) { const uint8_t* s = src + d.x; for (uint32_t i = 0; i < lit; i++) p[i] = __ldg(s + i); }
+            if (lit <= 16) { const uint8_t* s = src + d.x; for (uint32_t i = 0; i < lit; i++) p[i] = (uint8_t)ldg_na_u8(s + i); }
             p += lit;
             if (off) {
                 p[0] = (uint8_t)off; p[1] = (uint8_t)(off >> 8);                                         // :1068

@@ -178,8 +178,8 @@ decompress_kernel(DecompressArgs a)
         if (lane == 0) s = (int)atomicAdd(counter, 1u);
         s = __shfl_sync(kFull, s, 0);
         if (s >= a.n_streams) break;
-        const int b0 = a.stream_first ? a.stream_first[s] : s;
-        const int b1 = a.stream_first ? a.stream_first[s + 1] : s + 1;
+        const int b0 = a.stream_first ? a.stream_first[s] : a.first_block + s;
+        const int b1 = a.stream_first ? a.stream_first[s + 1] : b0 + 1;
         DState* st = a.states ? reinterpret_cast<DState*>(a.states[s]) : nullptr;
         const uint8_t* dict_end = nullptr; uint32_t dict_len = 0;
         if (st && st->prev_len) { dict_len = st->prev_len; dict_end = st->tail + 65536; }

@@ -9,6 +9,7 @@ namespace b200lz4 {
 struct CompressArgs {
     const uint8_t* src; const int64_t* src_off; const int32_t* src_len; int n_blocks;
     const int32_t* stream_first; int n_streams; void* const* states;
+    int first_block;            // independent mode (stream_first == NULL): stream s is block first_block + s
     uint8_t* dst; const int64_t* dst_off; const int32_t* dst_cap; int32_t* out_len;
     int accel; int header;
     Scratch* scratch;
@@ -17,6 +18,7 @@ struct CompressArgs {
 struct DecompressArgs {
     const uint8_t* src; const int64_t* src_off; const int32_t* src_len; int n_blocks;
     const int32_t* stream_first; int n_streams; void* const* states;
+    int first_block;
     uint8_t* dst; const int64_t* dst_off; const int32_t* dst_cap; int32_t* out_len;
     int header; int max_block;
     Scratch* scratch;
