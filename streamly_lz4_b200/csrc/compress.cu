@@ -30,6 +30,8 @@
 //     offset, literal runs are copied per lane (short) or cooperatively (long, 128-bit).
 //
 // The compaction pass (compact.cu) then gathers the per-block slots into one stream.
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -67,6 +69,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint: do not burn issue slots while idle
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes)
 { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
@@ -136,6 +149,34 @@ __device__ __forceinline__ uint32_t warp_common_suffix(const uint8_t* a, const u
     }
 }
 
+// ---- shared-memory input window of the finder ---------------------------------
+// Four 128-byte lines of the input around ip (data ring, keyed by global line index & 3,
+// filled with cp.async one line ahead of use) plus the LZ4 hash of every position in them
+// (hash ring, computed 128 positions at a time by all lanes when a line lands).  The scalar
+// re-test path takes hash(ip-2), hash(ip) and the bytes it compares from these rings, so its
+// dependent chain is shared-memory latency only and a few dozen instructions long.
+//   invariant while ip is in line L:  lines L-1, L, L+1 complete, L+2 in flight;
+//   data readable for positions [lo_pos, ready_end), hashes valid for [lo_pos, ready_end - 4).
+// All accesses use explicit 32-bit shared-space addresses (ld.shared / st.shared).
+constexpr int kWinLines = 4, kWinWords = kWinLines * 32, kWinBytes = kWinLines * 128;
+
+__device__ __forceinline__ void cp_async_4(uint32_t smem_addr, const void* g)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{ asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
+
+// 4 bytes of the data ring at (truncated) global byte address a
+__device__ __forceinline__ uint32_t ring_ld32(uint32_t data_s, uint32_t a)
+{
+    return __funnelshift_r(lds32(data_s + (a & (kWinBytes - 4))), lds32(data_s + ((a + 4) & (kWinBytes - 4))), (a & 3) * 8);
+}
+
 struct BlockIn {
     const uint8_t* src; int n;
     const uint8_t* dict_end;    // one past the last dictionary byte (meaningful iff dict_len > 0)
@@ -145,39 +186,40 @@ struct BlockIn {
     int block;                  // block index (for the emitter)
 };
 
-// Producer side of the queue.
+// Producer side of the queue (finder warp).  The buffer being filled is always already acquired.
 struct Producer {
     Queue* q;
     uint32_t batch;     // batches pushed so far
     int fill;           // descriptors in the current buffer
+    uint32_t slot_s;    // shared address of the next descriptor slot
 
-    __device__ __forceinline__ void acquire()
-    {   // wait until the buffer we are about to fill has been drained
+    __device__ __forceinline__ void begin()
+    {   // wait until the buffer we are about to fill has been drained, point at its first slot
         const uint32_t b = batch & 1, t = batch >> 1;
         if (t) mbar_wait(&q->empty[b], (t - 1) & 1);
+        slot_s = smem_u32(&q->desc[b][0]);
+        fill = 0;
     }
     __device__ __forceinline__ void push(uint32_t lit_pos, uint32_t lit_len, uint32_t mcode, uint32_t off, int block)
     {
-        if (fill == 0) acquire();
-        const uint32_t b = batch & 1;
-        if (lane_id() == 0) q->desc[b][fill] = make_uint4(lit_pos, lit_len, mcode, off);
-        fill++;
-        if (fill == kQueueDepth) flush(block, 0);
+        if (lane_id() == 0) sts128(slot_s, lit_pos, lit_len, mcode, off);
+        slot_s += 16;
+        if (++fill == kQueueDepth) flush(block, 0);
     }
     __device__ __forceinline__ void flush(int block, int flags)
     {
         if (fill == 0 && flags == 0) return;
-        if (fill == 0) acquire();
         const uint32_t b = batch & 1;
         if (lane_id() == 0) { q->count[b] = fill | flags; q->block[b] = block; }
         __syncwarp();
         if (lane_id() == 0) mbar_arrive(&q->full[b]);
-        batch++; fill = 0;
+        batch++;
+        begin();
     }
 };
 
 // Match finder for one block: pushes sequence descriptors, ends with the final-literals descriptor.
-__device__ void find_block(const BlockIn& in, uint32_t* table, Producer& out,
+__device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t data_s, const uint32_t hash_s, Producer& out,
                            const uint32_t off0, const uint32_t step0)
 {
     const uint32_t lane = lane_id();
@@ -188,68 +230,139 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, Producer& out,
     const uint32_t low_index = S - in.dict_len;                             // prefixIdxLimit, :879
     const int mfl = n - kMfLimit + 1;          // mflimitPlusOne as an index
     const int mlimit = n - kLastLiterals;      // matchlimit
+    const uint32_t table_s = smem_u32(table);
     int anchor = 0;
 
     if (n >= kMinLength) {
+        // ---- window state (see the invariant above)
+        const uintptr_t base = reinterpret_cast<uintptr_t>(src), end = base + (uintptr_t)n;
+        const uint32_t g32 = (uint32_t)base;
+        const uint32_t glane = g32 + 4 * lane;
+        uintptr_t cur_line = ~uintptr_t(0) - 8;
+        int lo_pos = 0, ready_end = 0, trigger = -1;
         uint32_t pf_next = 0;                  // next input byte not yet requested into L2
-        uint32_t l1_line = 0xFFFFFFFFu;
+
+        auto issue = [&](uintptr_t line) {     // one 4-byte cp.async per lane; lines outside the block are not touched
+            if ((line << 7) < end && ((line + 1) << 7) > base)
+                cp_async_4(data_s + (uint32_t)(((line & (kWinLines - 1)) * 32 + lane) * 4),
+                           reinterpret_cast<const void*>((line << 7) + 4 * lane));
+            cp_async_commit();
+        };
+        auto hash_round = [&](int p0) {        // hashes of the 128 positions from p0 on ((g32 + p0) % 4 == 0)
+            const uint32_t a = glane + (uint32_t)p0;
+            const uint32_t w0 = lds32(data_s + (a & (kWinBytes - 4))), w1 = lds32(data_s + ((a + 4) & (kWinBytes - 4)));
+            const uint32_t h0 = hash5(w0, w1 & 0xFFu);
+            const uint32_t h1 = hash5(__funnelshift_r(w0, w1, 8), (w1 >> 8) & 0xFFu);
+            const uint32_t h2 = hash5(__funnelshift_r(w0, w1, 16), (w1 >> 16) & 0xFFu);
+            const uint32_t h3 = hash5(__funnelshift_r(w0, w1, 24), w1 >> 24);
+            sts64(hash_s + ((a & (kWinBytes - 1)) << 1), h0 | (h1 << 16), h2 | (h3 << 16));
+        };
+        auto move_window = [&](int ip) {       // (re)centre the window on ip's line
+            const uintptr_t L = (base + (uintptr_t)ip) >> 7;
+            __syncwarp();
+            cp_async_wait<0>();
+            __syncwarp();
+            if (L == cur_line + 1) {           // steady state: line L+1 has just landed
+                hash_round(ready_end - 4);
+                ready_end += 128;
+                const int lo = (int)(((L - 1) << 7) - base);
+                lo_pos = lo_pos > lo ? lo_pos : lo;
+            } else {                           // jump: reload L-1, L, L+1
+                issue(L - 1); issue(L); issue(L + 1);
+                cp_async_wait<0>();
+                __syncwarp();
+                const long long lo = (long long)((L - 1) << 7) - (long long)base;
+                const int p0 = (int)lo;
+                hash_round(p0); hash_round(p0 + 128); hash_round(p0 + 256);
+                lo_pos = lo < 0 ? 0 : p0;
+                ready_end = p0 + 384;
+            }
+            issue(L + 2);
+            __syncwarp();
+            cur_line = L;
+            trigger = (int)(((L + 1) << 7) - base);
+            // keep the next kPrefetchAhead bytes of input on their way into L2
+            if ((uint32_t)ip + kPrefetchAhead > pf_next) {
+                if (pf_next < (uint32_t)ip) pf_next = (uint32_t)ip & ~(kPrefetchChunk - 1);
+                if (pf_next < (uint32_t)n) {
+                    const uintptr_t pbase = (base + pf_next) & ~uintptr_t(15);
+                    const uint32_t room = (uint32_t)n - pf_next;
+                    const uint32_t bytes = room < kPrefetchChunk ? (room & ~15u) : kPrefetchChunk;
+                    if (lane == 0 && bytes) prefetch_l2_bulk(reinterpret_cast<const void*>(pbase), bytes);
+                    pf_next += kPrefetchChunk;
+                }
+            }
+        };
+
         if (lane == 0) { uint2 v = ldg_5bytes(src); table[hash5(v.x, v.y)] = S; }   // :924
         __syncwarp();
         int ip = 1;                            // :925  (search runs start here)
         bool after_match = false;
         bool narrow = false;                   // adaptive probe-window width
         for (;;) {
-            // ---- keep the next kPrefetchAhead bytes of input on their way into L2
-            if (pf_next < (uint32_t)ip) pf_next = (uint32_t)ip & ~(kPrefetchChunk - 1);
-            if ((uint32_t)ip + kPrefetchAhead > pf_next && pf_next < (uint32_t)n) {
-                uintptr_t base = reinterpret_cast<uintptr_t>(src + pf_next) & ~uintptr_t(15);
-                uint32_t room = (uint32_t)n - pf_next;
-                uint32_t bytes = room < kPrefetchChunk ? (room & ~15u) : kPrefetchChunk;
-                if (lane == 0 && bytes) prefetch_l2_bulk(reinterpret_cast<const void*>(base), bytes);
-                pf_next += kPrefetchChunk;
-            }
-
-            {   // pull the next two 128-byte lines into L1 ahead of the scalar path
-                const uint32_t line = (uint32_t)((reinterpret_cast<uintptr_t>(src) + (uint32_t)ip) >> 7);
-                if (line != l1_line) {
-                    l1_line = line;
-                    if (lane < 2 && ip + 128 * (int)(lane + 1) < n) prefetch_l1(src + ip + 128 * (lane + 1));
-                }
-            }
-            int mpos; uint32_t midx; uint32_t mlen;     // match start, table index of its source, total length
-            bool have = false;
             if (after_match) {
-                // ---- scalar path: put(ip-2), re-test ip (cbits/lz4.c:1146, :1159-1196); ip == anchor here
-                uintptr_t a = reinterpret_cast<uintptr_t>(src + ip - 2);
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-                const uint32_t sh = (uint32_t)(a & 3) * 8;
-                const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-                const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);   // bytes ip-2 .. ip+5
-                const uint32_t h2 = hash5(v0, v1 & 0xFFu);
-                const uint32_t seq = __funnelshift_r(v0, v1, 16);                                   // bytes ip .. ip+3
-                const uint32_t h = hash5(seq, (v1 >> 16) & 0xFFu);
-                const uint32_t cur = S + (uint32_t)ip;
-                // every lane performs the same three accesses in program order, so no warp sync is needed
-                table[h2] = cur - 2;                                                                 // :1146
-                const uint32_t m = table[h];
-                table[h] = cur;                                                                      // :1185
-                if (!(dict_small && m < low_index) && (m + kMaxDistance >= cur)) {                   // :1187-1188
-                    // verify + count in one 32-lane load: common prefix of ip.. and candidate..
-                    const bool in_dict = m < S;
-                    const uint8_t* cand = in_dict ? (in.dict_end - (S - m)) : (src + (m - S));
+                // ---- scalar path: put(ip-2), re-test ip (cbits/lz4.c:1146, :1159-1196); ip == anchor here.
+                // Loops for as long as a match immediately follows a match.
+                for (;;) {
+                    if (ip >= trigger) move_window(ip);
+                    const uint32_t a2 = g32 + (uint32_t)ip;
+                    const uint32_t h = lds16(hash_s + ((a2 << 1) & (2 * kWinBytes - 2)));
+                    const uint32_t h2 = lds16(hash_s + (((a2 - 2) << 1) & (2 * kWinBytes - 2)));
+                    const uint32_t cur = S + (uint32_t)ip;
+                    // every lane performs the same three accesses in program order: no warp sync needed
+                    sts32(table_s + h2 * 4, cur - 2);                                                // :1146
+                    const uint32_t m = lds32(table_s + h * 4);
+                    sts32(table_s + h * 4, cur);                                                     // :1185
+                    if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) break;            // :1187-1188
+                    // verify + count in one 32-lane step: common prefix of ip.. and candidate..
                     uint32_t cap = (uint32_t)(mlimit - ip);
-                    if (in_dict) cap = min(cap, (uint32_t)(in.dict_end - cand));
-                    uint32_t L = warp_common_prefix(src + ip, cand, cap);
-                    if (L >= 4) {                                                                    // :1189
-                        if (in_dict && L == cap && (int)(ip + L) < mlimit)                           // :1085-1089
+                    uint32_t L;
+                    if (m >= S) {
+                        const int cpos = (int)(m - S);
+                        const uint32_t cap1 = min(cap, 128u);
+                        const uint32_t at = lane * 4;
+                        uint32_t x = 0xFFu;                                 // lanes wholly past cap1 read nothing
+                        if (at < cap1) {
+                            const uint32_t mine = ring_ld32(data_s, glane + (uint32_t)ip);
+                            const uint32_t theirs = (cpos >= lo_pos) ? ring_ld32(data_s, glane + (uint32_t)cpos)
+                                                                     : ldg_u32_unaligned(src + cpos + at);
+                            x = mine ^ theirs;
+                        }
+                        const uint32_t nb = x ? ((uint32_t)(__ffs(x) - 1) >> 3) : 4u;
+                        const uint32_t sb = __ballot_sync(kFull, (nb < 4) || (at + 4 >= cap1));   // never empty
+                        const uint32_t res = __shfl_sync(kFull, at + nb, __ffs(sb) - 1);
+                        L = res < cap1 ? res : cap1;
+                        if (res >= cap1 && cap > 128u)
+                            L += warp_common_prefix(src + ip + 128, src + cpos + 128, cap - 128u);
+                    } else {                                                                         // candidate in the dictionary
+                        const uint8_t* cand = in.dict_end - (S - m);
+                        cap = min(cap, (uint32_t)(in.dict_end - cand));
+                        L = warp_common_prefix(src + ip, cand, cap);
+                        if (L >= 4 && L == cap && (int)(ip + L) < mlimit)                            // :1085-1089
                             L += warp_common_prefix(src + ip + L, src, (uint32_t)(mlimit - (ip + (int)L)));
-                        have = true; mpos = ip; midx = m; mlen = L;
                     }
+                    if (L < 4) break;                                                                // :1189
+                    out.push((uint32_t)ip, 0u, L - 4, cur - m, in.block);
+                    ip += (int)L;
+                    anchor = ip;
+                    if (ip >= mfl) goto tail;                                                        // :1143
                 }
-                if (!have) ip++;                                                                     // :1200
+                ip++;                                                                                // :1200
             }
-            if (!have) {
+            // ---- keep the next kPrefetchAhead bytes of input on their way into L2 (search regime)
+            if ((uint32_t)ip + kPrefetchAhead > pf_next && pf_next < (uint32_t)n) {
+                if (pf_next < (uint32_t)ip) pf_next = (uint32_t)ip & ~(kPrefetchChunk - 1);
+                if (pf_next < (uint32_t)n) {
+                    const uintptr_t pbase = (base + pf_next) & ~uintptr_t(15);
+                    const uint32_t room = (uint32_t)n - pf_next;
+                    const uint32_t bytes = room < kPrefetchChunk ? (room & ~15u) : kPrefetchChunk;
+                    if (lane == 0 && bytes) prefetch_l2_bulk(reinterpret_cast<const void*>(pbase), bytes);
+                    pf_next += kPrefetchChunk;
+                }
+            }
+            {
                 // ---- speculative probe windows (cbits/lz4.c:956-1014), run starts at ip
+                int mpos = 0; uint32_t midx = 0;
                 long long jbase = 0;
                 uint32_t width = narrow ? 4u : 32u;
                 bool found = false; int hit_index = 0;
@@ -272,7 +385,7 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, Producer& out,
                     const uint32_t fwd = __shfl_sync(kFull, cur, from_lane);
                     bool ok = false; uint32_t m = 0;
                     if (valid) {
-                        m = lower ? fwd : table[h];
+                        m = lower ? fwd : lds32(table_s + h * 4);
                         if (!(dict_small && m < low_index) && (m + kMaxDistance >= cur)) {           // :1001-1006
                             const uint8_t* c = (m < S) ? (in.dict_end - (S - m)) : (src + (m - S));  // :985-993
                             ok = (ldg_u32_unaligned(c) == seq);                                      // :1009
@@ -285,7 +398,7 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, Producer& out,
                     const int ncommit = min(w + 1, nvalid);
                     if ((int)lane < ncommit) {                          // ordered commit: last writer per bucket
                         const uint32_t grp = peers & (ncommit >= 32 ? kFull : ((1u << ncommit) - 1u));
-                        if ((31 - __clz(grp)) == (int)lane) table[h] = cur;                          // :998
+                        if ((31 - __clz(grp)) == (int)lane) sts32(table_s + h * 4, cur);             // :998
                     }
                     __syncwarp();
                     if (w < 32) {
@@ -315,28 +428,29 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, Producer& out,
                 uint32_t L = 4 + warp_common_prefix(src + mip + 4, cand + 4, cap - 4);
                 if (in_dict && L == cap && mip + (int)L < mlimit)
                     L += warp_common_prefix(src + mip + L, src, (uint32_t)(mlimit - (mip + (int)L)));
-                midx = (S + (uint32_t)mpos) - midx;     // from here on: the offset
-                mpos = mip; mlen = L;
-                out.push((uint32_t)anchor, (uint32_t)(mpos - anchor), mlen - 4, midx, in.block);
-            } else {
-                out.push((uint32_t)anchor, 0u, mlen - 4, (S + (uint32_t)mpos) - midx, in.block);
+                out.push((uint32_t)anchor, (uint32_t)(mip - anchor), L - 4, (S + (uint32_t)mpos) - midx, in.block);
+                ip = mip + (int)L;
+                anchor = ip;
+                if (ip >= mfl) break;                                                                // :1143
+                after_match = true;
             }
-            ip = mpos + (int)mlen;
-            anchor = ip;
-            if (ip >= mfl) break;                                                                    // :1143
-            after_match = true;
         }
+    tail:
+        cp_async_wait<0>();             // nothing of this block's window may land after the next block starts
+        __syncwarp();
     }
     // last literals, :1204-1231
     out.push((uint32_t)anchor, (uint32_t)(n - anchor), 0u, 0u, in.block);
 }
 
-__device__ void finder_main(const CompressArgs& a, uint32_t* table, Queue* q)
+__device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ring, uint16_t* hring, Queue* q)
 {
     const uint32_t lane = lane_id();
     uint32_t* counter = &a.scratch->work_counter[0];
     const int accel = a.accel < 1 ? 1 : (a.accel > kAccelMax ? kAccelMax : a.accel);   // :1577-1578
-    Producer out{q, 0, 0};
+    Producer out{q, 0, 0, 0};
+    out.begin();
+    const uint32_t data_s = smem_u32(ring), hash_s = smem_u32(hring);
     long long off0; int step0;
     probe_schedule(lane, accel, off0, step0);           // first window of every search run
 
@@ -378,7 +492,7 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, Queue* q)
                 if (dict_len >= 1 && dict_len <= 3) dict_len = 0;                            // :1581-1587
                 BlockIn in{src, n, dict_end, dict_len, offset, accel, b};
                 if (n > 0) offset += (uint32_t)n;                                            // :918 (n == 0 never reaches it, :1263-1273)
-                find_block(in, table, out, (uint32_t)off0, (uint32_t)step0);
+                find_block(in, table, data_s, hash_s, out, (uint32_t)off0, (uint32_t)step0);
                 __syncwarp();
                 dict_end = src + n; dict_len = (uint32_t)n;                                  // :1633-1634
                 last_src = src; last_n = n;
@@ -421,7 +535,7 @@ __device__ void emitter_main(const CompressArgs& a, Queue* q)
     bool failed = false;
     for (;;) {
         const uint32_t b = batch & 1, t = batch >> 1;
-        mbar_wait(&q->full[b], t & 1);
+        while (!mbar_test(&q->full[b], t & 1)) __nanosleep(1000);      // idle emitters must not steal issue slots from finders
         const int cnt_flags = q->count[b];
         const int blk = q->block[b];
         const int cnt = cnt_flags & 0xFFFF;
@@ -501,6 +615,8 @@ compress_kernel(CompressArgs a)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* tables = reinterpret_cast<uint32_t*>(smem_raw);
     Queue* queues = reinterpret_cast<Queue*>(smem_raw + kPairs * kHashEntries * sizeof(uint32_t));
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw + kPairs * kHashEntries * sizeof(uint32_t) + kPairs * sizeof(Queue));
+    uint16_t* hrings = reinterpret_cast<uint16_t*>(rings + kPairs * kWinWords);
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t pair = warp & (kPairs - 1);
     if (threadIdx.x < kPairs) {
@@ -509,7 +625,7 @@ compress_kernel(CompressArgs a)
         mbar_init(&q->empty[0], 1); mbar_init(&q->empty[1], 1);
     }
     __syncthreads();
-    if (warp < kPairs) finder_main(a, tables + pair * kHashEntries, &queues[pair]);
+    if (warp < kPairs) finder_main(a, tables + pair * kHashEntries, rings + pair * kWinWords, hrings + pair * kWinBytes, &queues[pair]);
     else emitter_main(a, &queues[pair]);
     // last CTA out resets the work counter so the scratch stays zeroed for the next launch
     __syncthreads();
@@ -524,7 +640,8 @@ compress_kernel(CompressArgs a)
 cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
 {
     static int sm_counts[64] = {0};     // per device: SM count, 0 = kernel not configured there yet
-    const size_t smem = kPairs * kHashEntries * sizeof(uint32_t) + kPairs * sizeof(Queue);
+    const size_t smem = kPairs * kHashEntries * sizeof(uint32_t) + kPairs * sizeof(Queue) + kPairs * kWinWords * sizeof(uint32_t)
+                        + kPairs * kWinBytes * sizeof(uint16_t);
     int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!sm_counts[dev]) {
@@ -533,6 +650,11 @@ cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
         e = cudaFuncSetAttribute(compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         sm_counts[dev] = n;
+        if (getenv("B200LZ4_DEBUG")) {
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, compress_kernel, kPairs * 64, smem);
+            fprintf(stderr, "[b200lz4] compress_kernel: %zu B dynamic smem, %d CTAs/SM, %d SMs\n", smem, occ, n);
+        }
     }
     const int sm_count = sm_counts[dev];
     if (a.n_streams <= 0) return cudaSuccess;
