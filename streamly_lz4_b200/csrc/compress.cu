@@ -40,7 +40,7 @@ namespace b200lz4 {
 namespace {
 
 constexpr int kPairs = 4;                        // stream-owning warp pairs per CTA
-constexpr int kQueueDepth = 32;                  // descriptors per queue buffer
+constexpr int kQueueDepth = 16;                  // descriptors per queue buffer
 constexpr uint32_t kPrefetchAhead = 16384;       // bytes of input kept ahead in L2
 constexpr uint32_t kPrefetchChunk = 4096;
 
@@ -171,12 +171,6 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm 
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
 { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
 
-// 4 bytes of the data ring at (truncated) global byte address a
-__device__ __forceinline__ uint32_t ring_ld32(uint32_t data_s, uint32_t a)
-{
-    return __funnelshift_r(lds32(data_s + (a & (kWinBytes - 4))), lds32(data_s + ((a + 4) & (kWinBytes - 4))), (a & 3) * 8);
-}
-
 struct BlockIn {
     const uint8_t* src; int n;
     const uint8_t* dict_end;    // one past the last dictionary byte (meaningful iff dict_len > 0)
@@ -218,9 +212,14 @@ struct Producer {
     }
 };
 
+// (x & mask) | base in one LOP3 (base must have no bits inside mask: rings are aligned to their size)
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t mask, uint32_t base)
+{ uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(x), "r"(mask), "r"(base)); return d; }
+
 // Match finder for one block: pushes sequence descriptors, ends with the final-literals descriptor.
+// data_s (512-byte aligned) / hash_s (1024-byte aligned): shared addresses of this finder's rings.
 __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t data_s, const uint32_t hash_s, Producer& out,
-                           const uint32_t off0, const uint32_t step0)
+                           const uint32_t off0, const uint32_t step0, const uint32_t off1, const uint32_t step1)
 {
     const uint32_t lane = lane_id();
     const uint8_t* const src = in.src;
@@ -242,6 +241,10 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
         int lo_pos = 0, ready_end = 0, trigger = -1;
         uint32_t pf_next = 0;                  // next input byte not yet requested into L2
 
+        auto ring32 = [&](uint32_t a) {        // 4 bytes of the data ring at truncated global address a
+            return __funnelshift_r(lds32(and_or(a, kWinBytes - 4, data_s)), lds32(and_or(a + 4, kWinBytes - 4, data_s)), a << 3);
+        };
+        auto hash_at = [&](uint32_t a) { return lds16(and_or(a << 1, 2 * kWinBytes - 2, hash_s)); };
         auto issue = [&](uintptr_t line) {     // one 4-byte cp.async per lane; lines outside the block are not touched
             if ((line << 7) < end && ((line + 1) << 7) > base)
                 cp_async_4(data_s + (uint32_t)(((line & (kWinLines - 1)) * 32 + lane) * 4),
@@ -250,12 +253,22 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
         };
         auto hash_round = [&](int p0) {        // hashes of the 128 positions from p0 on ((g32 + p0) % 4 == 0)
             const uint32_t a = glane + (uint32_t)p0;
-            const uint32_t w0 = lds32(data_s + (a & (kWinBytes - 4))), w1 = lds32(data_s + ((a + 4) & (kWinBytes - 4)));
+            const uint32_t w0 = lds32(and_or(a, kWinBytes - 4, data_s)), w1 = lds32(and_or(a + 4, kWinBytes - 4, data_s));
             const uint32_t h0 = hash5(w0, w1 & 0xFFu);
             const uint32_t h1 = hash5(__funnelshift_r(w0, w1, 8), (w1 >> 8) & 0xFFu);
             const uint32_t h2 = hash5(__funnelshift_r(w0, w1, 16), (w1 >> 16) & 0xFFu);
             const uint32_t h3 = hash5(__funnelshift_r(w0, w1, 24), w1 >> 24);
-            sts64(hash_s + ((a & (kWinBytes - 1)) << 1), h0 | (h1 << 16), h2 | (h3 << 16));
+            sts64(and_or(a << 1, 2 * kWinBytes - 8, hash_s), h0 | (h1 << 16), h2 | (h3 << 16));
+        };
+        auto l2_prefetch = [&](int ip) {       // keep the next kPrefetchAhead bytes of input on their way into L2
+            if (pf_next < (uint32_t)ip) pf_next = (uint32_t)ip & ~(kPrefetchChunk - 1);
+            if (pf_next < (uint32_t)n) {
+                const uintptr_t pbase = (base + pf_next) & ~uintptr_t(15);
+                const uint32_t room = (uint32_t)n - pf_next;
+                const uint32_t bytes = room < kPrefetchChunk ? (room & ~15u) : kPrefetchChunk;
+                if (lane == 0 && bytes) prefetch_l2_bulk(reinterpret_cast<const void*>(pbase), bytes);
+            }
+            pf_next += kPrefetchChunk;
         };
         auto move_window = [&](int ip) {       // (re)centre the window on ip's line
             const uintptr_t L = (base + (uintptr_t)ip) >> 7;
@@ -281,17 +294,56 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
             __syncwarp();
             cur_line = L;
             trigger = (int)(((L + 1) << 7) - base);
-            // keep the next kPrefetchAhead bytes of input on their way into L2
-            if ((uint32_t)ip + kPrefetchAhead > pf_next) {
-                if (pf_next < (uint32_t)ip) pf_next = (uint32_t)ip & ~(kPrefetchChunk - 1);
-                if (pf_next < (uint32_t)n) {
-                    const uintptr_t pbase = (base + pf_next) & ~uintptr_t(15);
-                    const uint32_t room = (uint32_t)n - pf_next;
-                    const uint32_t bytes = room < kPrefetchChunk ? (room & ~15u) : kPrefetchChunk;
-                    if (lane == 0 && bytes) prefetch_l2_bulk(reinterpret_cast<const void*>(pbase), bytes);
-                    pf_next += kPrefetchChunk;
-                }
+            if ((uint32_t)ip + kPrefetchAhead > pf_next) l2_prefetch(ip);
+        };
+
+        // Scalar probe at position p (every lane computes the same thing; the only 32-wide step is the
+        // verify+count).  kRetest: the post-match probe, which first inserts p-2 and has no literals.
+        // On a hit fills mip / mlen / dist and returns true.
+        int mip = 0; uint32_t mlen = 0, dist = 0;
+        auto scalar_probe = [&](int p, bool retest) -> bool {
+            if (p >= trigger) move_window(p);
+            const uint32_t ap = g32 + (uint32_t)p;
+            const uint32_t mine = ring32(glane + (uint32_t)p);      // lane's 4 bytes of p.. (issued early: overlaps the table chain)
+            const uint32_t h = hash_at(ap);
+            const uint32_t cur = S + (uint32_t)p;
+            // every lane performs the same accesses in program order: no warp sync needed
+            if (retest) sts32(table_s + hash_at(ap - 2) * 4, cur - 2);                             // :1146
+            const uint32_t m = lds32(table_s + h * 4);
+            sts32(table_s + h * 4, cur);                                                             // :998 / :1185
+            if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) return false;             // :1001-1006 / :1187-1188
+            uint32_t cap = (uint32_t)(mlimit - p);
+            uint32_t L;
+            const uint8_t* cand;
+            uint32_t room_c;                    // bytes available before the candidate (catch-up limit)
+            if (m >= S) {
+                const int cpos = (int)(m - S);
+                cand = src + cpos; room_c = (uint32_t)cpos;
+                const uint32_t cap1 = min(cap, 128u);
+                const uint32_t at = lane * 4;
+                uint32_t x = 0xFFu;                                 // lanes wholly past cap1 read nothing
+                if (at < cap1)
+                    x = mine ^ ((cpos >= lo_pos) ? ring32(glane + (uint32_t)cpos) : ldg_u32_unaligned(cand + at));
+                const uint32_t nb = min((uint32_t)(__ffs(x) - 1) >> 3, 4u);   // x == 0 -> 4
+                const uint32_t sb = __ballot_sync(kFull, (nb < 4) || (at + 4 >= cap1));   // never empty
+                const uint32_t res = __shfl_sync(kFull, at + nb, __ffs(sb) - 1);
+                L = res < cap1 ? res : cap1;
+                if (res >= cap1 && cap > 128u) L += warp_common_prefix(src + p + 128, cand + 128, cap - 128u);
+            } else {                                                                                 // candidate in the dictionary
+                cand = in.dict_end - (S - m); room_c = in.dict_len - (S - m);
+                cap = min(cap, (uint32_t)(in.dict_end - cand));
+                L = warp_common_prefix(src + p, cand, cap);
+                if (L >= 4 && L == cap && (int)(p + L) < mlimit)                                     // :1085-1089
+                    L += warp_common_prefix(src + p + L, src, (uint32_t)(mlimit - (p + (int)L)));
             }
+            if (L < 4) return false;                                                                 // :1009 / :1189
+            uint32_t back = 0;
+            if (!retest) {                      // catch up (cbits/lz4.c:1019): usually nothing to do
+                const uint32_t maxback = min((uint32_t)(p - anchor), room_c);
+                if (maxback && __ldg(src + p - 1) == __ldg(cand - 1)) back = warp_common_suffix(src + p, cand, maxback);
+            }
+            mip = p - (int)back; mlen = L + back; dist = cur - m;
+            return true;
         };
 
         if (lane == 0) { uint2 v = ldg_5bytes(src); table[hash5(v.x, v.y)] = S; }   // :924
@@ -299,76 +351,37 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
         int ip = 1;                            // :925  (search runs start here)
         bool after_match = false;
         bool narrow = false;                   // adaptive probe-window width
+        bool first_scalar = false;             // predictor: the previous run hit on its first probe
         for (;;) {
+            bool have = false;
             if (after_match) {
-                // ---- scalar path: put(ip-2), re-test ip (cbits/lz4.c:1146, :1159-1196); ip == anchor here.
+                // ---- put(ip-2), re-test ip (cbits/lz4.c:1146, :1159-1196); ip == anchor here.
                 // Loops for as long as a match immediately follows a match.
-                for (;;) {
-                    if (ip >= trigger) move_window(ip);
-                    const uint32_t a2 = g32 + (uint32_t)ip;
-                    const uint32_t h = lds16(hash_s + ((a2 << 1) & (2 * kWinBytes - 2)));
-                    const uint32_t h2 = lds16(hash_s + (((a2 - 2) << 1) & (2 * kWinBytes - 2)));
-                    const uint32_t cur = S + (uint32_t)ip;
-                    // every lane performs the same three accesses in program order: no warp sync needed
-                    sts32(table_s + h2 * 4, cur - 2);                                                // :1146
-                    const uint32_t m = lds32(table_s + h * 4);
-                    sts32(table_s + h * 4, cur);                                                     // :1185
-                    if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) break;            // :1187-1188
-                    // verify + count in one 32-lane step: common prefix of ip.. and candidate..
-                    uint32_t cap = (uint32_t)(mlimit - ip);
-                    uint32_t L;
-                    if (m >= S) {
-                        const int cpos = (int)(m - S);
-                        const uint32_t cap1 = min(cap, 128u);
-                        const uint32_t at = lane * 4;
-                        uint32_t x = 0xFFu;                                 // lanes wholly past cap1 read nothing
-                        if (at < cap1) {
-                            const uint32_t mine = ring_ld32(data_s, glane + (uint32_t)ip);
-                            const uint32_t theirs = (cpos >= lo_pos) ? ring_ld32(data_s, glane + (uint32_t)cpos)
-                                                                     : ldg_u32_unaligned(src + cpos + at);
-                            x = mine ^ theirs;
-                        }
-                        const uint32_t nb = x ? ((uint32_t)(__ffs(x) - 1) >> 3) : 4u;
-                        const uint32_t sb = __ballot_sync(kFull, (nb < 4) || (at + 4 >= cap1));   // never empty
-                        const uint32_t res = __shfl_sync(kFull, at + nb, __ffs(sb) - 1);
-                        L = res < cap1 ? res : cap1;
-                        if (res >= cap1 && cap > 128u)
-                            L += warp_common_prefix(src + ip + 128, src + cpos + 128, cap - 128u);
-                    } else {                                                                         // candidate in the dictionary
-                        const uint8_t* cand = in.dict_end - (S - m);
-                        cap = min(cap, (uint32_t)(in.dict_end - cand));
-                        L = warp_common_prefix(src + ip, cand, cap);
-                        if (L >= 4 && L == cap && (int)(ip + L) < mlimit)                            // :1085-1089
-                            L += warp_common_prefix(src + ip + L, src, (uint32_t)(mlimit - (ip + (int)L)));
-                    }
-                    if (L < 4) break;                                                                // :1189
-                    out.push((uint32_t)ip, 0u, L - 4, cur - m, in.block);
-                    ip += (int)L;
+                while (scalar_probe(ip, true)) {
+                    out.push((uint32_t)ip, 0u, mlen - 4, dist, in.block);
+                    ip += (int)mlen;
                     anchor = ip;
                     if (ip >= mfl) goto tail;                                                        // :1143
                 }
                 ip++;                                                                                // :1200
             }
-            // ---- keep the next kPrefetchAhead bytes of input on their way into L2 (search regime)
-            if ((uint32_t)ip + kPrefetchAhead > pf_next && pf_next < (uint32_t)n) {
-                if (pf_next < (uint32_t)ip) pf_next = (uint32_t)ip & ~(kPrefetchChunk - 1);
-                if (pf_next < (uint32_t)n) {
-                    const uintptr_t pbase = (base + pf_next) & ~uintptr_t(15);
-                    const uint32_t room = (uint32_t)n - pf_next;
-                    const uint32_t bytes = room < kPrefetchChunk ? (room & ~15u) : kPrefetchChunk;
-                    if (lane == 0 && bytes) prefetch_l2_bulk(reinterpret_cast<const void*>(pbase), bytes);
-                    pf_next += kPrefetchChunk;
-                }
+            if ((uint32_t)ip + kPrefetchAhead > pf_next) l2_prefetch(ip);
+            // ---- a search run starts at ip (cbits/lz4.c:956-1014)
+            long long jbase = 0;
+            if (first_scalar) {                // probe 0 of the run on the scalar path
+                if (ip + 1 > mfl) break;                                                             // :969
+                have = scalar_probe(ip, false);
+                jbase = 1;
             }
-            {
-                // ---- speculative probe windows (cbits/lz4.c:956-1014), run starts at ip
+            if (!have) {
+                // ---- speculative probe windows
                 int mpos = 0; uint32_t midx = 0;
-                long long jbase = 0;
                 uint32_t width = narrow ? 4u : 32u;
                 bool found = false; int hit_index = 0;
                 for (;;) {
                     long long off; int step;
                     if (jbase == 0) { off = off0; step = (int)step0; }
+                    else if (jbase == 1) { off = off1; step = (int)step1; }
                     else probe_schedule(jbase + lane, in.accel, off, step);
                     const long long pos64 = (long long)ip + off;
                     const bool active = lane < width;
@@ -412,9 +425,10 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
                 }
                 if (!found) break;
                 narrow = (in.accel > 16) && (hit_index < 3);
+                first_scalar = (hit_index == 0);
 
                 // catch up (cbits/lz4.c:1019), then count (:1076-1095)
-                int mip = mpos;
+                mip = mpos;
                 const bool in_dict = midx < S;
                 const uint8_t* cand = in_dict ? (in.dict_end - (S - midx)) : (src + (midx - S));
                 {
@@ -428,12 +442,13 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
                 uint32_t L = 4 + warp_common_prefix(src + mip + 4, cand + 4, cap - 4);
                 if (in_dict && L == cap && mip + (int)L < mlimit)
                     L += warp_common_prefix(src + mip + L, src, (uint32_t)(mlimit - (mip + (int)L)));
-                out.push((uint32_t)anchor, (uint32_t)(mip - anchor), L - 4, (S + (uint32_t)mpos) - midx, in.block);
-                ip = mip + (int)L;
-                anchor = ip;
-                if (ip >= mfl) break;                                                                // :1143
-                after_match = true;
+                mlen = L; dist = (S + (uint32_t)mpos) - midx;
             }
+            out.push((uint32_t)anchor, (uint32_t)(mip - anchor), mlen - 4, dist, in.block);
+            ip = mip + (int)mlen;
+            anchor = ip;
+            if (ip >= mfl) break;                                                                    // :1143
+            after_match = true;
         }
     tail:
         cp_async_wait<0>();             // nothing of this block's window may land after the next block starts
@@ -451,8 +466,9 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ri
     Producer out{q, 0, 0, 0};
     out.begin();
     const uint32_t data_s = smem_u32(ring), hash_s = smem_u32(hring);
-    long long off0; int step0;
-    probe_schedule(lane, accel, off0, step0);           // first window of every search run
+    long long off0, off1; int step0, step1;
+    probe_schedule(lane, accel, off0, step0);           // first window of a search run, starting at probe 0
+    probe_schedule(lane + 1, accel, off1, step1);       // ... starting at probe 1 (probe 0 was taken by the scalar path)
 
     for (;;) {
         int s = 0;
@@ -492,7 +508,7 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ri
                 if (dict_len >= 1 && dict_len <= 3) dict_len = 0;                            // :1581-1587
                 BlockIn in{src, n, dict_end, dict_len, offset, accel, b};
                 if (n > 0) offset += (uint32_t)n;                                            // :918 (n == 0 never reaches it, :1263-1273)
-                find_block(in, table, data_s, hash_s, out, (uint32_t)off0, (uint32_t)step0);
+                find_block(in, table, data_s, hash_s, out, (uint32_t)off0, (uint32_t)step0, (uint32_t)off1, (uint32_t)step1);
                 __syncwarp();
                 dict_end = src + n; dict_len = (uint32_t)n;                                  // :1633-1634
                 last_src = src; last_n = n;
@@ -612,11 +628,13 @@ __device__ void emitter_main(const CompressArgs& a, Queue* q)
 __global__ void __launch_bounds__(kPairs * 64)
 compress_kernel(CompressArgs a)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t* tables = reinterpret_cast<uint32_t*>(smem_raw);
-    Queue* queues = reinterpret_cast<Queue*>(smem_raw + kPairs * kHashEntries * sizeof(uint32_t));
-    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw + kPairs * kHashEntries * sizeof(uint32_t) + kPairs * sizeof(Queue));
-    uint16_t* hrings = reinterpret_cast<uint16_t*>(rings + kPairs * kWinWords);
+    extern __shared__ __align__(16) uint8_t smem_dyn[];
+    // layout (from a 1024-byte aligned start): hash rings | data rings | tables | queues
+    uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint16_t* hrings = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw + kPairs * kWinBytes * sizeof(uint16_t));
+    uint32_t* tables = rings + kPairs * kWinWords;
+    Queue* queues = reinterpret_cast<Queue*>(tables + kPairs * kHashEntries);
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t pair = warp & (kPairs - 1);
     if (threadIdx.x < kPairs) {
@@ -641,7 +659,7 @@ cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
 {
     static int sm_counts[64] = {0};     // per device: SM count, 0 = kernel not configured there yet
     const size_t smem = kPairs * kHashEntries * sizeof(uint32_t) + kPairs * sizeof(Queue) + kPairs * kWinWords * sizeof(uint32_t)
-                        + kPairs * kWinBytes * sizeof(uint16_t);
+                        + kPairs * kWinBytes * sizeof(uint16_t) + 1024 /* alignment slack */;
     int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!sm_counts[dev]) {
