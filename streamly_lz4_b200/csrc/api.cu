@@ -162,15 +162,21 @@ int plan_chunks(const int64_t* off, const int32_t* len, int n, const int32_t* fi
 {
     int64_t total = 0;
     for (int i = 0; i < n; i++) total += len[i];
-    const int64_t target = std::max<int64_t>(int64_t(24) << 20, (total + kMaxChunks - 1) / kMaxChunks);
+    // Chunk k becomes ready when its H2D copy lands and finishes one block latency later, so the end of the
+    // call is "last byte arrives + block latency + D2H of the last chunk": keep the last chunk small.
+    static const double kShare[kMaxChunks] = {0.14, 0.20, 0.20, 0.20, 0.18, 0.08};
+    const bool small = total < (int64_t(48) << 20);
     int k = 0, unit = 0;
     const int units = first ? ns : n;
+    int64_t done = 0;
     while (unit < units) {
         Chunk c; c.s0 = unit; c.b0 = first ? first[unit] : unit;
-        int64_t bytes = 0;
-        while (unit < units && (bytes < target || k == kMaxChunks - 1)) {
+        double upto = 0;
+        for (int q = 0; q <= k; q++) upto += kShare[q];
+        const int64_t target = (small || k == kMaxChunks - 1) ? total : (int64_t)(upto * (double)total);
+        while (unit < units && (done < target || k == kMaxChunks - 1 || small)) {
             const int u0 = first ? first[unit] : unit, u1 = first ? first[unit + 1] : unit + 1;
-            for (int i = u0; i < u1; i++) bytes += len[i];
+            for (int i = u0; i < u1; i++) done += len[i];
             unit++;
         }
         c.s1 = unit; c.b1 = first ? first[unit] : unit;

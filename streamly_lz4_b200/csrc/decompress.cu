@@ -10,7 +10,9 @@
 // 128-bit loads; tokens / offsets / length bytes are parsed from shared memory with
 // warp-uniform control flow (length-extension runs are summed 32 bytes at a time with
 // a ballot), literals and matches are copied cooperatively by the 32 lanes, with
-// overlapping matches (offset < length) handled as a periodic source.
+// overlapping matches (offset < length) handled as a periodic source.  The last KiB of
+// output is mirrored in a shared-memory ring so that matches with small offsets are served
+// from shared memory rather than through an L2 round trip to bytes just stored.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -18,44 +20,54 @@ namespace b200lz4 {
 
 namespace {
 
-constexpr int kWinBytes = 512;          // per-warp staging window
+constexpr int kWinBytes = 512;          // per-warp staging window of the compressed stream
+constexpr int kRingBytes = 1024;        // per-warp ring of the most recent output bytes
+constexpr uint32_t kRingReach = kRingBytes - 64;   // matches with offset <= this read the ring
 constexpr int kDecWarps = 4;
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v)
+{ asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+
+// Staging window over the compressed payload: 512 bytes of it live in shared memory.
 struct Window {
-    const uint8_t* smem;        // this warp's window (kWinBytes)
-    uint4* smem4;
+    uint32_t win_s;             // shared address of the window
     const uint8_t* src;         // payload
     int src_len;
-    long long base;             // payload index held in smem[0] (16-byte aligned in global space)
+    int base;                   // payload index held at win_s (16-byte aligned in global space; may be slightly negative)
 
     __device__ __forceinline__ void load(int ip)
     {
         const uint32_t lane = lane_id();
-        uintptr_t g = reinterpret_cast<uintptr_t>(src + ip);
-        base = (long long)ip - (long long)(g & 15);
-        long long at = base + 16 * (long long)lane;
+        base = ip - (int)(reinterpret_cast<uintptr_t>(src + ip) & 15);
+        const int at = base + 16 * (int)lane;
         __syncwarp();
-        if (at < (long long)src_len)
-            smem4[lane] = __ldg(reinterpret_cast<const uint4*>(src + at));
+        if (at < src_len) sts128(win_s + 16 * lane, __ldg(reinterpret_cast<const uint4*>(src + at)));
         __syncwarp();
     }
+    // make [ip, ip + need) readable (need <= 64)
     __device__ __forceinline__ void ensure(int ip, int need)
     {
-        if ((long long)ip + need > base + kWinBytes || (long long)ip < base) load(ip);
+        if ((uint32_t)(ip - base) > (uint32_t)(kWinBytes - need)) load(ip);
     }
-    __device__ __forceinline__ uint32_t at(int ip) const { return smem[(long long)ip - base]; }
+    __device__ __forceinline__ uint32_t at(int ip) const { return lds8(win_s + (uint32_t)(ip - base)); }
     __device__ __forceinline__ bool holds(int ip, uint32_t len) const
-    { return (long long)ip >= base && (long long)ip + (long long)len <= base + kWinBytes; }
+    { return (uint32_t)(ip - base) + len <= (uint32_t)kWinBytes; }
 };
 
 // Decode one block.  dict_end/dict_len: previous output of the stream (dict_len == 0: none).
-__device__ int decode_block(Window& w, uint8_t* dst, int cap, const uint8_t* dict_end, uint32_t dict_len)
+// ring_s: shared address of this warp's output ring; ring[q & (kRingBytes-1)] mirrors dst[q] for
+// ring_lo <= q < op, so that matches with small offsets (the common case on compressible data) are
+// served from shared memory instead of an L2 round trip to bytes this warp has just stored.
+__device__ int decode_block(Window& w, const uint32_t ring_s, uint8_t* dst, int cap, const uint8_t* dict_end, uint32_t dict_len)
 {
     const uint32_t lane = lane_id();
     const int src_len = w.src_len;
     const bool check_offset = dict_len < 65536u;                       // cbits/lz4.c:1764
-    int ip = 0;
-    long long op = 0;
+    int ip = 0, op = 0;
+    int ring_lo = 0;
     if (cap == 0) {                                                    // :1781-1785
         if (src_len != 1) return -1;
         w.load(0);
@@ -72,33 +84,37 @@ __device__ int decode_block(Window& w, uint8_t* dst, int cap, const uint8_t* dic
             if (ip >= lim) return -ip - 1;                             // initial_error
             for (;;) {
                 w.ensure(ip, 32);
-                int p = ip + (int)lane;
-                uint32_t s = (p < lim) ? w.at(p) : 0u;
-                bool stop = (p >= lim - 1) || (s != 255u);             // reading position lim-1 ends the run (loop_error keeps the sum)
-                uint32_t sb = __ballot_sync(kFull, stop);
+                const int p = ip + (int)lane;
+                const uint32_t s = (p < lim) ? w.at(p) : 0u;
+                const bool stop = (p >= lim - 1) || (s != 255u);       // reading position lim-1 ends the run (loop_error keeps the sum)
+                const uint32_t sb = __ballot_sync(kFull, stop);
                 if (sb) {
-                    int t = __ffs(sb) - 1;
-                    uint32_t last = __shfl_sync(kFull, s, t);
-                    len += 255u * (uint32_t)t + last;
+                    const int t = __ffs(sb) - 1;
+                    len += 255u * (uint32_t)t + __shfl_sync(kFull, s, t);
                     ip += t + 1;
                     break;
                 }
                 len += 255u * 32u; ip += 32;
             }
+            if (len > 0x7FFFFFFFu) return -ip - 1;                     // cannot be a valid run; keeps the int arithmetic below exact
         }
         // end rule, :1991-2047
-        if (op + (long long)len > (long long)cap - kMfLimit || (long long)ip + (long long)len > (long long)src_len - (2 + 1 + kLastLiterals)) {
-            if ((long long)ip + (long long)len != (long long)src_len || op + (long long)len > (long long)cap) return -ip - 1;
-            if (w.holds(ip, len)) { for (uint32_t i = lane; i < len; i += 32) dst[op + i] = (uint8_t)w.at(ip + (int)i); }
-            else warp_copy_ro(dst + op, w.src + ip, len);
-            op += len;
-            break;
-        }
+        const bool last = ((long long)op + len > (long long)cap - kMfLimit) || ((long long)ip + len > (long long)src_len - (2 + 1 + kLastLiterals));
+        if (last && ((long long)ip + len != (long long)src_len || (long long)op + len > (long long)cap)) return -ip - 1;
         if (len) {
-            if (w.holds(ip, len)) { for (uint32_t i = lane; i < len; i += 32) dst[op + i] = (uint8_t)w.at(ip + (int)i); }
-            else warp_copy_ro(dst + op, w.src + ip, len);
-            ip += (int)len; op += len;
+            if (len <= 64 && w.holds(ip, len)) {
+                for (uint32_t i = lane; i < len; i += 32) {
+                    const uint32_t b = w.at(ip + (int)i);
+                    dst[op + (int)i] = (uint8_t)b;
+                    sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
+                }
+            } else {
+                warp_copy_ro(dst + op, w.src + ip, len);
+                ring_lo = op + (int)len;                               // the ring does not mirror this run
+            }
+            ip += (int)len; op += (int)len;
         }
+        if (last) break;
         w.ensure(ip, 34);
         const uint32_t dist = w.at(ip) | (w.at(ip + 1) << 8); ip += 2;  // :2055
         uint32_t mlen = token & 15;
@@ -106,12 +122,12 @@ __device__ int decode_block(Window& w, uint8_t* dst, int cap, const uint8_t* dic
             const int lim = src_len - kLastLiterals + 1;
             for (;;) {
                 w.ensure(ip, 32);
-                int p = ip + (int)lane;
-                uint32_t s = (p < src_len) ? w.at(p) : 0u;
-                bool stop = (p >= src_len) || (s != 255u);
-                uint32_t sb = __ballot_sync(kFull, stop);
+                const int p = ip + (int)lane;
+                const uint32_t s = (p < src_len) ? w.at(p) : 0u;
+                const bool stop = (p >= src_len) || (s != 255u);
+                const uint32_t sb = __ballot_sync(kFull, stop);
                 if (sb) {
-                    int t = __ffs(sb) - 1;
+                    const int t = __ffs(sb) - 1;
                     if (ip + t + 1 >= lim) return -(ip + t + 1) - 1;   // loop_error
                     mlen += 255u * (uint32_t)t + __shfl_sync(kFull, s, t);
                     ip += t + 1;
@@ -122,41 +138,85 @@ __device__ int decode_block(Window& w, uint8_t* dst, int cap, const uint8_t* dic
             }
         }
         mlen += kMinMatch;
-        const long long from = op - (long long)dist;
-        if (check_offset && from + (long long)dict_len < 0) return -ip - 1;      // :2073
-        if (op + (long long)mlen > (long long)cap - kLastLiterals) return -ip - 1; // :2076-2078, :2139
+        const int from = op - (int)dist;
+        if (check_offset && (long long)from + (long long)dict_len < 0) return -ip - 1;   // :2073
+        if ((long long)op + mlen > (long long)cap - kLastLiterals) return -ip - 1;        // :2076-2078, :2139
         if (dist == 0) return -ip - 1;     // format violation (the reference copies garbage here, :2122-2130)
-        __syncwarp();                      // earlier stores of this warp are ordered before the loads below
+        __syncwarp();                      // earlier stores of this warp (global and ring) are ordered before the loads below
         uint8_t* out = dst + op;
-        if (from >= 0) {
-            const uint8_t* m = dst + from;
-            if (dist >= mlen) {                                // no overlap
-                for (uint32_t i = lane; i < mlen; i += 32) out[i] = m[i];
-            } else if (dist >= 32) {                           // overlap, period >= one round
+        if (from >= ring_lo && dist <= kRingReach) {
+            // ---- source is in the ring
+            const uint32_t rsrc = (uint32_t)from, rdst = (uint32_t)op;
+            if (dist >= 32) {
                 for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
-                    uint32_t i = i0 + lane;
-                    if (i < mlen) out[i] = m[i];
-                    __syncwarp();
+                    const uint32_t i = i0 + lane;
+                    if (i < mlen) {
+                        const uint32_t b = lds8(ring_s + ((rsrc + i) & (kRingBytes - 1)));
+                        out[i] = (uint8_t)b;
+                        sts8(ring_s + ((rdst + i) & (kRingBytes - 1)), b);
+                    }
+                    if (dist < mlen) __syncwarp();             // later rounds read what this round wrote
                 }
-            } else {                                           // short period: source is dist bytes repeated
-                uint32_t k = lane % dist, adv = 32 % dist;
+            } else {                                           // short period: the source is dist bytes repeated
+                // the pattern is taken into registers first: a long run would overwrite its ring slots
+                const uint32_t pat = lds8(ring_s + ((rsrc + (lane < dist ? lane : 0u)) & (kRingBytes - 1)));
+                uint32_t k = lane % dist;
+                const uint32_t adv = 32 % dist;
+                for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    const uint32_t b = __shfl_sync(kFull, pat, k);
+                    if (i < mlen) {
+                        out[i] = (uint8_t)b;
+                        sts8(ring_s + ((rdst + i) & (kRingBytes - 1)), b);
+                    }
+                    k += adv; if (k >= dist) k -= dist;
+                }
+            }
+        } else if (from >= 0) {
+            // ---- source in this block's output, read back through L2
+            const uint8_t* m = dst + from;
+            if (dist >= 32) {
+                for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    if (i < mlen) {
+                        const uint32_t b = m[i];
+                        out[i] = (uint8_t)b;
+                        sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
+                    }
+                    if (dist < mlen) __syncwarp();
+                }
+            } else {
+                uint32_t k = lane % dist;
+                const uint32_t adv = 32 % dist;
                 for (uint32_t i = lane; i < mlen; i += 32) {
-                    out[i] = m[k];
+                    const uint32_t b = m[k];
+                    out[i] = (uint8_t)b;
+                    sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
                     k += adv; if (k >= dist) k -= dist;
                 }
             }
         } else if (dist >= 32) {                               // starts in the previous output (:2075-2100)
             for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
-                uint32_t i = i0 + lane;
-                if (i < mlen) { long long f = from + i; out[i] = (f < 0) ? dict_end[f] : dst[f]; }
+                const uint32_t i = i0 + lane;
+                if (i < mlen) {
+                    const int f = from + (int)i;
+                    const uint32_t b = (f < 0) ? dict_end[f] : dst[f];
+                    out[i] = (uint8_t)b;
+                    sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
+                }
                 __syncwarp();
             }
         } else {                                               // dist < 32 and op < dist: a handful of bytes, serial
-            if (lane == 0) for (uint32_t i = 0; i < mlen; i++) { long long f = from + i; out[i] = (f < 0) ? dict_end[f] : dst[f]; }
+            if (lane == 0) for (uint32_t i = 0; i < mlen; i++) {
+                const int f = from + (int)i;
+                const uint32_t b = (f < 0) ? dict_end[f] : dst[f];
+                out[i] = (uint8_t)b;
+                sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
+            }
         }
-        op += mlen;
+        op += (int)mlen;
     }
-    return (int)op;
+    return op;
 }
 
 __device__ __forceinline__ int read_le32(const uint8_t* p)
@@ -166,12 +226,13 @@ __global__ void __launch_bounds__(kDecWarps * 32)
 decompress_kernel(DecompressArgs a)
 {
     __shared__ uint4 windows[kDecWarps][kWinBytes / 16];
+    __shared__ uint4 rings[kDecWarps][kRingBytes / 16];
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
     uint32_t* counter = &a.scratch->work_counter[2];
     Window w;
-    w.smem4 = windows[warp];
-    w.smem = reinterpret_cast<const uint8_t*>(windows[warp]);
+    w.win_s = smem_u32(windows[warp]);
+    const uint32_t ring_s = smem_u32(rings[warp]);
 
     for (;;) {
         int s = 0;
@@ -197,7 +258,7 @@ decompress_kernel(DecompressArgs a)
                 if (a.dst_cap && cap > a.dst_cap[b]) ok = false;
                 if (ok) {
                     w.src = arr + a.header; w.src_len = comp_len; w.base = 0;
-                    r = decode_block(w, out, cap, dict_end, dict_len);
+                    r = decode_block(w, ring_s, out, cap, dict_end, dict_len);
                     __syncwarp();
                 }
             }
