@@ -5,14 +5,26 @@
 // decode_full_block, {noDict | usingExtDict with the previous output})
 // (cbits/lz4.c:1737-2165; the safe loop :1929-2151 defines the accept/reject rules).
 //
-// Organisation: one WARP per stream (independent mode: one block).  The compressed
-// bytes are staged through a per-warp shared-memory window filled with coalesced
-// 128-bit loads; tokens / offsets / length bytes are parsed from shared memory with
-// warp-uniform control flow (length-extension runs are summed 32 bytes at a time with
-// a ballot), literals and matches are copied cooperatively by the 32 lanes, with
-// overlapping matches (offset < length) handled as a periodic source.  The last KiB of
-// output is mirrored in a shared-memory ring so that matches with small offsets are served
-// from shared memory rather than through an L2 round trip to bytes just stored.
+// Organisation: one CTA of two warps per stream (independent mode: per block).
+//
+//   PARSER warp -- walks the token chain, the only inherently serial part
+//     (token -> literal length -> offset -> match length -> next token).  The compressed
+//     payload is streamed into a 4 KiB shared-memory ring with cp.async (16 bytes per lane,
+//     well ahead of the parse point), so one step of the chain costs a couple of
+//     shared-memory round trips.  The parser applies every accept/reject rule of the safe
+//     decoder (it tracks the output position) and hands (literal start, literal length,
+//     match length, offset) descriptors to the copier through a double-buffered queue
+//     (mbarrier full/empty handshakes).
+//   COPIER warp -- executes up to 32 sequences at a time.  Output is assembled in an 8 KiB
+//     shared-memory ring and flushed to global memory with 128-bit stores, so matches with
+//     near offsets never touch L2 and global writes are coalesced.
+//       phase A  lane j copies the literals of sequence j (input ring -> output ring) and,
+//                if the match of sequence j only reads bytes produced before this batch,
+//                its match bytes as well: 32 sequences in parallel;
+//       phase B  matches that read bytes produced inside the batch run in order, each one
+//                copied by all lanes (overlapping matches are a periodic source);
+//       bulk     sequences with a long literal run or a long match travel alone and are
+//                copied cooperatively global -> global.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -20,72 +32,251 @@ namespace b200lz4 {
 
 namespace {
 
-constexpr int kWinBytes = 512;          // per-warp staging window of the compressed stream
-constexpr int kRingBytes = 1024;        // per-warp ring of the most recent output bytes
-constexpr uint32_t kRingReach = kRingBytes - 64;   // matches with offset <= this read the ring
-constexpr int kDecWarps = 4;
+constexpr int kInRing = 4096;            // bytes of compressed payload resident in shared memory
+constexpr int kFill = 512;               // ring fill unit (32 lanes x 16 bytes)
+constexpr int kOutRing = 8192;           // bytes of recent output resident in shared memory
+constexpr int kQDepth = 32;              // descriptors per queue buffer
+constexpr uint32_t kShortLit = 32;       // sequences within these limits take the lane-parallel path
+constexpr uint32_t kShortMatch = 64;
+constexpr int kWindowSeqs = 11;          // most sequences one 32-byte parse window can hold (3 bytes each)
+// A batch is at most kQDepth short sequences: <= 32 * (1 + 32 + 2 + 1) = 1152 compressed bytes (plus skipped
+// length bytes, which nobody reads again) and <= 32 * (32 + 64) = 3072 output bytes.
+
+constexpr int kCountMask = 0xFFFF;
+constexpr int kBulk = 1 << 16;           // the batch is one sequence to be copied cooperatively
+constexpr int kBegin = 1 << 17;          // first batch of a block
+constexpr int kStreamBegin = 1 << 18;    // ... of the first block of a stream
+constexpr int kStreamEnd = 1 << 19;      // with kEndBlock: last block of the stream
+constexpr int kEndBlock = 1 << 30;       // block finished; result[] holds what to report
+constexpr int kTerminate = 1 << 29;
+
+struct __align__(16) DQueue {
+    uint4 desc[2][kQDepth];              // {literal start (ring space), literal length, match length (0 = none), offset}
+    unsigned long long full[2], empty[2];
+    int count[2];
+    int block[2];
+    int stream[2];
+    int result[2];
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts128(uint32_t a, uint4 v)
-{ asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{ uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{ asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* g)
+{ asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Staging window over the compressed payload: 512 bytes of it live in shared memory.
-struct Window {
-    uint32_t win_s;             // shared address of the window
-    const uint8_t* src;         // payload
-    int src_len;
-    int base;                   // payload index held at win_s (16-byte aligned in global space; may be slightly negative)
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 
-    __device__ __forceinline__ void load(int ip)
-    {
-        const uint32_t lane = lane_id();
-        base = ip - (int)(reinterpret_cast<uintptr_t>(src + ip) & 15);
-        const int at = base + 16 * (int)lane;
-        __syncwarp();
-        if (at < src_len) sts128(win_s + 16 * lane, __ldg(reinterpret_cast<const uint4*>(src + at)));
-        __syncwarp();
+__device__ __forceinline__ int read_le32(const uint8_t* p)
+{ return (int)((uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24)); }
+
+// Header fields and the checks of decompressChunk (src/Streamly/Internal/LZ4.hs:303-318): both warps
+// derive the same block geometry from the descriptor arrays.
+struct BlockGeom { const uint8_t* payload; int comp_len; int cap; uint8_t* out; bool ok; };
+__device__ __forceinline__ BlockGeom block_geom(const DecompressArgs& a, int b)
+{
+    BlockGeom g;
+    const uint8_t* arr = a.src + a.src_off[b];
+    const int avail = a.src_len[b] - a.header;
+    g.payload = arr + a.header; g.out = a.dst + a.dst_off[b];
+    g.comp_len = 0; g.cap = 0; g.ok = false;
+    if (avail >= 0) {
+        g.comp_len = a.header >= 4 ? read_le32(arr) : avail;                  // LZ4.hs:303
+        g.cap = a.header == 8 ? read_le32(arr + 4) : a.max_block;             // LZ4.hs:189-198
+        g.ok = g.comp_len > 0 && g.comp_len == avail && g.cap >= 0;           // LZ4.hs:309-318 (array length bounds the read)
+        if (a.dst_cap && g.cap > a.dst_cap[b]) g.ok = false;
     }
-    // make [ip, ip + need) readable (need <= 64)
-    __device__ __forceinline__ void ensure(int ip, int need)
-    {
-        if ((uint32_t)(ip - base) > (uint32_t)(kWinBytes - need)) load(ip);
+    return g;
+}
+
+// ------------------------------------------------------------------ parser ----
+
+struct Parser {
+    DQueue* q;
+    uint32_t ring_s;            // shared address of the input ring
+    // queue producer state
+    uint32_t batch;             // batches published so far
+    int fill;                   // descriptors in the buffer being filled
+    uint32_t slot_s;            // shared address of the next descriptor slot
+    int flags;                  // flags to attach to the buffer being filled
+    // batch bounds (ring space / output space)
+    int cur_start;              // ring-space position where the current batch starts
+    int prev_start;             // ... where the previously published batch starts
+    bool prev_pending;          // that batch may still be read by the copier
+    // input ring state (ring space: payload index + skew, so that 16-byte granules are aligned in both spaces)
+    const uint8_t* gbase;       // global address of ring-space position 0
+    int end;                    // ring-space end of the payload
+    int issued_end, ready_end;  // fills issued / complete and visible, ring space (multiples of kFill)
+    int block, stream;
+
+    __device__ __forceinline__ void begin()
+    {   // wait until the buffer we are about to fill has been drained
+        const uint32_t b = batch & 1, t = batch >> 1;
+        if (t) mbar_wait(&q->empty[b], (t - 1) & 1);
+        slot_s = smem_u32(&q->desc[b][0]);
+        fill = 0;
     }
-    __device__ __forceinline__ uint32_t at(int ip) const { return lds8(win_s + (uint32_t)(ip - base)); }
-    __device__ __forceinline__ bool holds(int ip, uint32_t len) const
-    { return (uint32_t)(ip - base) + len <= (uint32_t)kWinBytes; }
+    // publish the current buffer (possibly empty) with extra flags
+    __device__ __forceinline__ void publish(int extra, int result, int ip)
+    {
+        const uint32_t b = batch & 1;
+        cp_async_wait_all();            // literal bytes of this batch must have landed before the copier is told
+        if (lane_id() == 0) { q->count[b] = fill | flags | extra; q->block[b] = block; q->stream[b] = stream; q->result[b] = result; }
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&q->full[b]);
+        ready_end = issued_end;
+        batch++;
+        flags = 0;
+        prev_start = cur_start; prev_pending = true;
+        cur_start = ip;
+        begin();                        // the buffer of the batch before the one just published is now free ...
+        // ... so only the batch just published can still be pending
+    }
+    __device__ __forceinline__ void push(uint32_t lit_src, uint32_t lit, uint32_t mlen, uint32_t off)
+    {
+        if (lane_id() == 0) sts128(slot_s, lit_src, lit, mlen, off);
+        slot_s += 16;
+        fill++;
+    }
+    __device__ __forceinline__ uint32_t at(int p) const { return lds8(ring_s + ((uint32_t)p & (kInRing - 1))); }
+
+    // issue ring fills ahead of ip as far as the copier's needs allow
+    __device__ __forceinline__ void top_up(int ip)
+    {
+        const int lo_needed = prev_pending ? prev_start : cur_start;
+        while (issued_end < end && issued_end - ip < 2048 && issued_end + kFill - kInRing <= lo_needed) {
+            const int p = issued_end + 16 * (int)lane_id();
+            if (p < end) cp_async_16(ring_s + ((uint32_t)p & (kInRing - 1)), gbase + p);
+            cp_async_commit();
+            issued_end += kFill;
+        }
+    }
+    // make ring bytes [.., need) readable, need <= ip + 64 (or report that the payload ends before)
+    __device__ void ensure(int ip, int need)
+    {
+        if (need <= ready_end) return;
+        if (ip >= issued_end) {                         // jumped over everything requested so far: restart at ip
+            cp_async_wait_all();
+            issued_end = ip & ~(kFill - 1);
+            ready_end = issued_end;
+        }
+        for (;;) {
+            top_up(ip);
+            if (need <= issued_end || issued_end >= end) break;
+            // blocked: the ring would overwrite bytes the copier may still read
+            if (prev_pending) {
+                const uint32_t pb = (batch - 1) & 1, t = (batch - 1) >> 1;
+                mbar_wait(&q->empty[pb], t & 1);
+                prev_pending = false;
+            } else {
+                publish(0, 0, ip);                      // the current batch itself pins the ring: hand it over
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        ready_end = issued_end;
+    }
 };
 
-// Decode one block.  dict_end/dict_len: previous output of the stream (dict_len == 0: none).
-// ring_s: shared address of this warp's output ring; ring[q & (kRingBytes-1)] mirrors dst[q] for
-// ring_lo <= q < op, so that matches with small offsets (the common case on compressible data) are
-// served from shared memory instead of an L2 round trip to bytes this warp has just stored.
-__device__ int decode_block(Window& w, const uint32_t ring_s, uint8_t* dst, int cap, const uint8_t* dict_end, uint32_t dict_len)
+// Parse one block; pushes descriptors; returns the value to report (bytes produced, or < 0).
+// Positions ip* are in ring space (payload index + skew).
+//
+// Two paths.  WINDOW: lane l decodes the 32 bytes from ip on as if a token started at ip + l (token, offset,
+// one optional length byte), then the true token chain is followed through the window with one shuffle
+// per sequence; the lanes on the chain write their descriptors side by side.  Only sequences without a
+// literal-length extension, with at most one match-length byte and a short match qualify, and only away
+// from the end of the block, where none of the end-of-block rules can fire.  SERIAL: everything else,
+// one sequence at a time with the complete rule set of the safe decoder.
+__device__ int parse_block(Parser& P, int skew, int src_len, int cap, uint32_t dict_len)
 {
     const uint32_t lane = lane_id();
-    const int src_len = w.src_len;
     const bool check_offset = dict_len < 65536u;                       // cbits/lz4.c:1764
-    int ip = 0, op = 0;
-    int ring_lo = 0;
+    const int iend = skew + src_len;                                   // ring-space end of the payload
+    const uint32_t ring_s = P.ring_s;
+    int ip = skew, op = 0;
+    P.end = iend;
+    P.issued_end = P.ready_end = skew & ~(kFill - 1);
+    P.cur_start = ip;
     if (cap == 0) {                                                    // :1781-1785
         if (src_len != 1) return -1;
-        w.load(0);
-        return w.at(0) == 0 ? 0 : -1;
+        P.ensure(ip, ip + 1);
+        return P.at(ip) == 0 ? 0 : -1;
     }
     if (src_len == 0) return -1;                                       // :1787
-    w.load(0);
     for (;;) {
-        w.ensure(ip, 64);
-        const uint32_t token = w.at(ip); ip++;
+        if (P.fill + kWindowSeqs > kQDepth) P.publish(0, 0, ip);
+        if (P.issued_end - ip < 1024) P.top_up(ip);
+        if (ip + 64 > P.ready_end) P.ensure(ip, ip + 64);
+        if (ip + 56 <= iend && op + 1024 <= cap) {
+            // ---- window path
+            const int p = ip + (int)lane;
+            const uint32_t tok = lds8(ring_s + ((uint32_t)p & (kInRing - 1)));
+            const uint32_t lit = tok >> 4, ml = tok & 15u;
+            const uint32_t o = (uint32_t)p + 1u + lit;                 // offset field, if lit < 15
+            const uint32_t b0 = lds8(ring_s + (o & (kInRing - 1)));
+            const uint32_t b1 = lds8(ring_s + ((o + 1) & (kInRing - 1)));
+            const uint32_t b2 = lds8(ring_s + ((o + 2) & (kInRing - 1)));
+            const uint32_t dist = b0 | (b1 << 8);                      // :2055
+            const bool ext = ml == 15u;
+            const uint32_t mlen = ext ? 19u + b2 : ml + 4u;            // one length byte b2 != 255, :2062-2067
+            const uint32_t nxt = lane + 3u + lit + (ext ? 1u : 0u);    // next token, relative to ip
+            const bool simple = lit < 15u && !(ext && b2 == 255u) && mlen <= kShortMatch;
+            const uint32_t packed = nxt | ((lit + mlen) << 8) | (simple ? 0u : 0x80000000u);
+            uint32_t cur = 0, real = 0;
+            int opr = op, my_op = 0;
+            for (;;) {
+                const uint32_t info = __shfl_sync(kFull, packed, cur);
+                if ((int)info < 0) break;
+                if (lane == cur) my_op = opr;
+                real |= 1u << cur;
+                opr += (int)((info >> 8) & 0xFFFFu);
+                cur = info & 0xFFu;
+                if (cur >= 32u) break;
+            }
+            if (real) {
+                const bool mine = (real >> lane) & 1u;
+                // rules that can fire here: offset beyond the dictionary start (:2073), zero offset
+                const bool bad = mine && (dist == 0u || (check_offset && (uint32_t)my_op + lit + dict_len < dist));
+                if (__ballot_sync(kFull, bad)) return -1;
+                const uint32_t rank = __popc(real & lanemask_lt());
+                if (mine) sts128(P.slot_s + 16u * rank, (uint32_t)p + 1u, lit, mlen, dist);
+                const int n = __popc(real);
+                P.slot_s += 16u * (uint32_t)n; P.fill += n;
+                op = opr; ip += (int)cur;
+                continue;
+            }
+        }
+        // ---- serial path: one sequence
+        const uint32_t token = P.at(ip); ip++;
         uint32_t len = token >> 4;
         if (len == 15) {                                               // :1977-1983 with reader :1707-1729
-            const int lim = src_len - 15;
-            if (ip >= lim) return -ip - 1;                             // initial_error
+            const int lim = iend - 15;
+            if (ip >= lim) return -1;                                  // initial_error
             for (;;) {
-                w.ensure(ip, 32);
+                P.ensure(ip, ip + 32);
                 const int p = ip + (int)lane;
-                const uint32_t s = (p < lim) ? w.at(p) : 0u;
+                const uint32_t s = (p < lim) ? P.at(p) : 0u;
                 const bool stop = (p >= lim - 1) || (s != 255u);       // reading position lim-1 ends the run (loop_error keeps the sum)
                 const uint32_t sb = __ballot_sync(kFull, stop);
                 if (sb) {
@@ -96,144 +287,68 @@ __device__ int decode_block(Window& w, const uint32_t ring_s, uint8_t* dst, int 
                 }
                 len += 255u * 32u; ip += 32;
             }
-            if (len > 0x7FFFFFFFu) return -ip - 1;                     // cannot be a valid run; keeps the int arithmetic below exact
+            if (len > 0x7FFFFFFFu) return -1;                          // cannot be a valid run; keeps the int arithmetic below exact
         }
         // end rule, :1991-2047
-        const bool last = ((long long)op + len > (long long)cap - kMfLimit) || ((long long)ip + len > (long long)src_len - (2 + 1 + kLastLiterals));
-        if (last && ((long long)ip + len != (long long)src_len || (long long)op + len > (long long)cap)) return -ip - 1;
-        if (len) {
-            if (len <= 64 && w.holds(ip, len)) {
-                for (uint32_t i = lane; i < len; i += 32) {
-                    const uint32_t b = w.at(ip + (int)i);
-                    dst[op + (int)i] = (uint8_t)b;
-                    sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
-                }
-            } else {
-                warp_copy_ro(dst + op, w.src + ip, len);
-                ring_lo = op + (int)len;                               // the ring does not mirror this run
+        const bool last = ((long long)op + len > (long long)cap - kMfLimit) || ((long long)ip + len > (long long)iend - (2 + 1 + kLastLiterals));
+        if (last && ((long long)ip + len != (long long)iend || (long long)op + len > (long long)cap)) return -1;
+        const bool bulk_lit = len > kShortLit;
+        if (last) {
+            if (len) {
+                if (bulk_lit) { if (P.fill) P.publish(0, 0, ip); P.push((uint32_t)ip, len, 0u, 0u); P.publish(kBulk, 0, ip + (int)len); }
+                else { P.ensure(ip, ip + (int)len); P.push((uint32_t)ip, len, 0u, 0u); }
             }
-            ip += (int)len; op += (int)len;
+            return op + (int)len;
         }
-        if (last) break;
-        w.ensure(ip, 34);
-        const uint32_t dist = w.at(ip) | (w.at(ip + 1) << 8); ip += 2;  // :2055
+        const int lit_src = ip;
+        ip += (int)len;
+        P.ensure(ip, ip + 34);
+        const uint32_t dist = P.at(ip) | (P.at(ip + 1) << 8); ip += 2;  // :2055
         uint32_t mlen = token & 15;
         if (mlen == 15) {                                              // :2062-2067
-            const int lim = src_len - kLastLiterals + 1;
+            const int lim = iend - kLastLiterals + 1;
             for (;;) {
-                w.ensure(ip, 32);
+                P.ensure(ip, ip + 32);
                 const int p = ip + (int)lane;
-                const uint32_t s = (p < src_len) ? w.at(p) : 0u;
-                const bool stop = (p >= src_len) || (s != 255u);
+                const uint32_t s = (p < iend) ? P.at(p) : 0u;
+                const bool stop = (p >= iend) || (s != 255u);
                 const uint32_t sb = __ballot_sync(kFull, stop);
                 if (sb) {
                     const int t = __ffs(sb) - 1;
-                    if (ip + t + 1 >= lim) return -(ip + t + 1) - 1;   // loop_error
+                    if (ip + t + 1 >= lim) return -1;                  // loop_error
                     mlen += 255u * (uint32_t)t + __shfl_sync(kFull, s, t);
                     ip += t + 1;
                     break;
                 }
-                if (ip + 32 >= lim) return -(ip + 32) - 1;
+                if (ip + 32 >= lim) return -1;
                 mlen += 255u * 32u; ip += 32;
             }
         }
         mlen += kMinMatch;
+        op += (int)len;
         const int from = op - (int)dist;
-        if (check_offset && (long long)from + (long long)dict_len < 0) return -ip - 1;   // :2073
-        if ((long long)op + mlen > (long long)cap - kLastLiterals) return -ip - 1;        // :2076-2078, :2139
-        if (dist == 0) return -ip - 1;     // format violation (the reference copies garbage here, :2122-2130)
-        __syncwarp();                      // earlier stores of this warp (global and ring) are ordered before the loads below
-        uint8_t* out = dst + op;
-        if (from >= ring_lo && dist <= kRingReach) {
-            // ---- source is in the ring
-            const uint32_t rsrc = (uint32_t)from, rdst = (uint32_t)op;
-            if (dist >= 32) {
-                for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    if (i < mlen) {
-                        const uint32_t b = lds8(ring_s + ((rsrc + i) & (kRingBytes - 1)));
-                        out[i] = (uint8_t)b;
-                        sts8(ring_s + ((rdst + i) & (kRingBytes - 1)), b);
-                    }
-                    if (dist < mlen) __syncwarp();             // later rounds read what this round wrote
-                }
-            } else {                                           // short period: the source is dist bytes repeated
-                // the pattern is taken into registers first: a long run would overwrite its ring slots
-                const uint32_t pat = lds8(ring_s + ((rsrc + (lane < dist ? lane : 0u)) & (kRingBytes - 1)));
-                uint32_t k = lane % dist;
-                const uint32_t adv = 32 % dist;
-                for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    const uint32_t b = __shfl_sync(kFull, pat, k);
-                    if (i < mlen) {
-                        out[i] = (uint8_t)b;
-                        sts8(ring_s + ((rdst + i) & (kRingBytes - 1)), b);
-                    }
-                    k += adv; if (k >= dist) k -= dist;
-                }
-            }
-        } else if (from >= 0) {
-            // ---- source in this block's output, read back through L2
-            const uint8_t* m = dst + from;
-            if (dist >= 32) {
-                for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    if (i < mlen) {
-                        const uint32_t b = m[i];
-                        out[i] = (uint8_t)b;
-                        sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
-                    }
-                    if (dist < mlen) __syncwarp();
-                }
-            } else {
-                uint32_t k = lane % dist;
-                const uint32_t adv = 32 % dist;
-                for (uint32_t i = lane; i < mlen; i += 32) {
-                    const uint32_t b = m[k];
-                    out[i] = (uint8_t)b;
-                    sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
-                    k += adv; if (k >= dist) k -= dist;
-                }
-            }
-        } else if (dist >= 32) {                               // starts in the previous output (:2075-2100)
-            for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                if (i < mlen) {
-                    const int f = from + (int)i;
-                    const uint32_t b = (f < 0) ? dict_end[f] : dst[f];
-                    out[i] = (uint8_t)b;
-                    sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
-                }
-                __syncwarp();
-            }
-        } else {                                               // dist < 32 and op < dist: a handful of bytes, serial
-            if (lane == 0) for (uint32_t i = 0; i < mlen; i++) {
-                const int f = from + (int)i;
-                const uint32_t b = (f < 0) ? dict_end[f] : dst[f];
-                out[i] = (uint8_t)b;
-                sts8(ring_s + ((uint32_t)(op + (int)i) & (kRingBytes - 1)), b);
-            }
+        if (check_offset && (long long)from + (long long)dict_len < 0) return -1;        // :2073
+        if ((long long)op + mlen > (long long)cap - kLastLiterals) return -1;             // :2076-2078, :2139
+        if (dist == 0) return -1;          // format violation (the reference copies garbage here, :2122-2130)
+        if (bulk_lit || mlen > kShortMatch) {
+            if (P.fill) P.publish(0, 0, lit_src);
+            P.push((uint32_t)lit_src, len, mlen, dist);
+            P.publish(kBulk, 0, ip);
+        } else {
+            P.push((uint32_t)lit_src, len, mlen, dist);
         }
         op += (int)mlen;
     }
-    return op;
 }
 
-__device__ __forceinline__ int read_le32(const uint8_t* p)
-{ return (int)((uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24)); }
-
-__global__ void __launch_bounds__(kDecWarps * 32)
-decompress_kernel(DecompressArgs a)
+__device__ void parser_main(const DecompressArgs& a, DQueue* q, uint32_t ring_s)
 {
-    __shared__ uint4 windows[kDecWarps][kWinBytes / 16];
-    __shared__ uint4 rings[kDecWarps][kRingBytes / 16];
     const uint32_t lane = lane_id();
-    const uint32_t warp = threadIdx.x >> 5;
     uint32_t* counter = &a.scratch->work_counter[2];
-    Window w;
-    w.win_s = smem_u32(windows[warp]);
-    const uint32_t ring_s = smem_u32(rings[warp]);
-
+    Parser P;
+    P.q = q; P.ring_s = ring_s; P.batch = 0; P.fill = 0; P.flags = 0; P.prev_pending = false; P.prev_start = 0; P.cur_start = 0;
+    P.block = -1; P.stream = -1;
+    P.begin();
     for (;;) {
         int s = 0;
         if (lane == 0) s = (int)atomicAdd(counter, 1u);
@@ -241,40 +356,270 @@ decompress_kernel(DecompressArgs a)
         if (s >= a.n_streams) break;
         const int b0 = a.stream_first ? a.stream_first[s] : a.first_block + s;
         const int b1 = a.stream_first ? a.stream_first[s + 1] : b0 + 1;
-        DState* st = a.states ? reinterpret_cast<DState*>(a.states[s]) : nullptr;
-        const uint8_t* dict_end = nullptr; uint32_t dict_len = 0;
-        if (st && st->prev_len) { dict_len = st->prev_len; dict_end = st->tail + 65536; }
-        const uint8_t* last_out = nullptr; int last_len = 0;
+        const DState* st = a.states ? reinterpret_cast<const DState*>(a.states[s]) : nullptr;
+        uint32_t dict_len = st ? st->prev_len : 0u;
         for (int b = b0; b < b1; b++) {
-            const uint8_t* arr = a.src + a.src_off[b];
-            const int alen = a.src_len[b];
-            const int avail = alen - a.header;
-            uint8_t* out = a.dst + a.dst_off[b];
+            const BlockGeom g = block_geom(a, b);
+            P.block = b; P.stream = s;
+            if (P.prev_pending) {       // the copier may still read literals of the previous block from the ring
+                const uint32_t pb = (P.batch - 1) & 1, t = (P.batch - 1) >> 1;
+                mbar_wait(&q->empty[pb], t & 1);
+                P.prev_pending = false;
+            }
+            P.flags = kBegin | (b == b0 ? kStreamBegin : 0);
             int r = -1;
-            if (avail >= 0) {
-                int comp_len = a.header >= 4 ? read_le32(arr) : avail;                 // LZ4.hs:303
-                int cap = a.header == 8 ? read_le32(arr + 4) : a.max_block;            // LZ4.hs:189-198
-                bool ok = comp_len > 0 && comp_len == avail && cap >= 0;               // LZ4.hs:309-318 (array length bounds the read)
-                if (a.dst_cap && cap > a.dst_cap[b]) ok = false;
-                if (ok) {
-                    w.src = arr + a.header; w.src_len = comp_len; w.base = 0;
-                    r = decode_block(w, ring_s, out, cap, dict_end, dict_len);
-                    __syncwarp();
+            if (g.ok) {
+                const int skew = (int)(reinterpret_cast<uintptr_t>(g.payload) & 15);
+                P.gbase = g.payload - skew;
+                r = parse_block(P, skew, g.comp_len, g.cap, dict_len);
+            }
+            P.publish(kEndBlock | (b == b1 - 1 ? kStreamEnd : 0), r, 0);
+            if (r > 0) dict_len = (uint32_t)r;                         // cbits/lz4.c:2353-2355
+        }
+    }
+    P.publish(kTerminate, 0, 0);
+}
+
+// ------------------------------------------------------------------ copier ----
+
+// coherent (not read-only-path) cooperative copy, non-overlapping, arbitrary alignment
+__device__ __forceinline__ void warp_copy_rw(uint8_t* dst, const uint8_t* src, uint32_t len)
+{
+    const uint32_t lane = lane_id();
+    if (len < 96) {
+        for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+        return;
+    }
+    uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+    if (lane < head) dst[lane] = src[lane];
+    dst += head; src += head; len -= head;
+    const uint32_t nvec = len >> 4;
+    uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+    const uint32_t sh = (uint32_t)(sa & 3) * 8;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+    uint4* dv = reinterpret_cast<uint4*>(dst);
+    if ((sa & 15) == 0) {
+        const uint4* sv = reinterpret_cast<const uint4*>(src);
+        for (uint32_t v = lane; v < nvec; v += 32) dv[v] = sv[v];
+    } else {
+        for (uint32_t v = lane; v < nvec; v += 32) {
+            const uint32_t* qd = sw + 4 * v;
+            uint32_t x0 = qd[0], x1 = qd[1], x2 = qd[2], x3 = qd[3], x4 = sh ? qd[4] : 0u;
+            dv[v] = make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh),
+                               __funnelshift_r(x2, x3, sh), __funnelshift_r(x3, x4, sh));
+        }
+    }
+    const uint32_t done = nvec << 4, tail = len - done;
+    if (lane < tail) dst[done + lane] = src[done + lane];
+}
+
+struct Copier {
+    uint32_t in_s, out_s;       // shared addresses of the rings
+    uint8_t* dst;               // output of the current block
+    uint32_t oskew;             // (address of dst) & 15: ring index of output position q is (q + oskew) & (kOutRing - 1)
+    int op;                     // output bytes produced so far
+    int flushed;                // output positions below this are in global memory
+    int ring_lo;                // output positions below this are NOT in the ring (bulk copies bypass it)
+    const uint8_t* dict_end; uint32_t dict_len;
+
+    __device__ __forceinline__ uint32_t oidx(int q) const { return out_s + (((uint32_t)q + oskew) & (kOutRing - 1)); }
+
+    // ring -> global for output positions [flushed, upto); unless `all`, stops at the last 16-byte boundary
+    __device__ void flush(int upto, bool all)
+    {
+        const uint32_t lane = lane_id();
+        int lo = flushed, hi = upto;
+        if (!all) hi = (int)((((uint32_t)upto + oskew) & ~15u) - oskew);
+        if (hi <= lo) return;
+        uint32_t head = (16u - (((uint32_t)lo + oskew) & 15u)) & 15u;
+        if (head > (uint32_t)(hi - lo)) head = (uint32_t)(hi - lo);
+        if (lane < head) dst[lo + (int)lane] = (uint8_t)lds8(oidx(lo + (int)lane));
+        lo += (int)head;
+        const uint32_t nvec = (uint32_t)(hi - lo) >> 4;
+        for (uint32_t v = lane; v < nvec; v += 32) {
+            const int qv = lo + (int)(v << 4);
+            *reinterpret_cast<uint4*>(dst + qv) = lds128(oidx(qv));
+        }
+        lo += (int)(nvec << 4);
+        const uint32_t tail = (uint32_t)(hi - lo);
+        if (lane < tail) dst[lo + (int)lane] = (uint8_t)lds8(oidx(lo + (int)lane));
+        flushed = hi;
+    }
+};
+
+__device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, uint32_t out_s)
+{
+    const uint32_t lane = lane_id();
+    Copier C;
+    C.in_s = in_s; C.out_s = out_s; C.dst = nullptr; C.oskew = 0; C.op = 0; C.flushed = 0; C.ring_lo = 0;
+    C.dict_end = nullptr; C.dict_len = 0;
+    const uint8_t* gbase = nullptr;         // global address of input ring-space position 0
+    const uint8_t* last_out = nullptr; int last_len = 0;
+    uint32_t batch = 0;
+    for (;;) {
+        const uint32_t b = batch & 1, t = batch >> 1;
+        mbar_wait(&q->full[b], t & 1);
+        const int cf = q->count[b];
+        const int blk = q->block[b];
+        const int cnt = cf & kCountMask;
+        if (cf & kTerminate) break;
+        uint4 d = make_uint4(0, 0, 0, 0);
+        if ((int)lane < cnt) d = q->desc[b][lane];
+        if (cf & kBegin) {
+            const BlockGeom g = block_geom(a, blk);
+            C.dst = g.out; C.oskew = (uint32_t)(reinterpret_cast<uintptr_t>(g.out) & 15);
+            C.op = 0; C.flushed = 0; C.ring_lo = 0;
+            gbase = g.payload - (reinterpret_cast<uintptr_t>(g.payload) & 15);
+            if (cf & kStreamBegin) {
+                const DState* st = a.states ? reinterpret_cast<const DState*>(a.states[q->stream[b]]) : nullptr;
+                C.dict_end = nullptr; C.dict_len = 0; last_out = nullptr; last_len = 0;
+                if (st && st->prev_len) { C.dict_len = st->prev_len; C.dict_end = st->tail + 65536; }
+            }
+        }
+        const int result = q->result[b];
+        const int stream = q->stream[b];
+        uint8_t* const dst = C.dst;
+
+        if (cf & kBulk) {
+            // ---- one long sequence, copied cooperatively global -> global
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q->empty[b]);
+            const uint32_t lit_src = __shfl_sync(kFull, d.x, 0), lit = __shfl_sync(kFull, d.y, 0);
+            const uint32_t mlen = __shfl_sync(kFull, d.z, 0), dist = __shfl_sync(kFull, d.w, 0);
+            C.flush(C.op, true);
+            __syncwarp();
+            if (lit) warp_copy_ro(dst + C.op, gbase + lit_src, lit);
+            int op = C.op + (int)lit;
+            __syncwarp();
+            if (mlen) {
+                const int from = op - (int)dist;
+                uint8_t* out = dst + op;
+                if (from < 0) {                                        // starts in the previous output (:2075-2100)
+                    for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        if (i < mlen) { const int f = from + (int)i; out[i] = (f < 0) ? C.dict_end[f] : dst[f]; }
+                        __syncwarp();
+                    }
+                } else if (dist >= mlen) {
+                    warp_copy_rw(out, dst + from, mlen);
+                } else if (dist >= 32) {                               // overlapping: rounds of one period each
+                    for (uint32_t done = 0; done < mlen; done += dist) {
+                        const uint32_t n = min(dist, mlen - done);
+                        warp_copy_rw(out + done, dst + from + done, n);
+                        __syncwarp();
+                    }
+                } else {                                               // short period: the source is dist bytes repeated
+                    const uint32_t pat = dst[from + (int)(lane < dist ? lane : 0u)];
+                    uint32_t k = lane % dist;
+                    const uint32_t adv = 32 % dist;
+                    for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        const uint32_t bb = __shfl_sync(kFull, pat, k);
+                        if (i < mlen) out[i] = (uint8_t)bb;
+                        k += adv; if (k >= dist) k -= dist;
+                    }
+                }
+                op += (int)mlen;
+            }
+            __syncwarp();
+            C.op = op; C.flushed = op; C.ring_lo = op;
+        } else if (cnt) {
+            // ---- up to 32 short sequences
+            const uint32_t lit = d.y, mlen = d.z, dist = d.w;
+            const uint32_t tot = lit + mlen;
+            uint32_t incl = tot;
+            #pragma unroll
+            for (int dl = 1; dl < 32; dl <<= 1) { uint32_t v = __shfl_up_sync(kFull, incl, dl); if ((int)lane >= dl) incl += v; }
+            const int op0 = C.op;
+            const int op1 = op0 + (int)__shfl_sync(kFull, incl, 31);
+            const int lit_dst = op0 + (int)(incl - tot);
+            const int m_dst = lit_dst + (int)lit;
+            const int from = m_dst - (int)dist;
+            C.flush(op0, false);                       // previous batches leave for global memory (128-bit stores)
+            const int ring_base = max(C.ring_lo, op1 - kOutRing);       // output positions >= this are in the ring; below: in global memory
+            // phase A: literals (lane per sequence)
+            for (uint32_t i = 0; i < lit; i++)
+                sts8(C.oidx(lit_dst + (int)i), lds8(in_s + ((d.x + i) & (kInRing - 1))));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q->empty[b]);  // descriptors are in registers and the input ring is no longer needed
+            // phase A: matches whose source was complete before this batch
+            const bool has_match = mlen != 0;
+            const bool indep = has_match && (from + (int)mlen <= op0);
+            if (indep) {
+                for (uint32_t i = 0; i < mlen; i++) {
+                    const int f = from + (int)i;
+                    uint32_t bb;
+                    if (f >= ring_base) bb = lds8(C.oidx(f));
+                    else if (f >= 0) bb = dst[f];
+                    else bb = C.dict_end[f];
+                    sts8(C.oidx(m_dst + (int)i), bb);
                 }
             }
-            if (lane == 0) a.out_len[b] = r;
-            if (r > 0) { dict_end = out + r; dict_len = (uint32_t)r; last_out = out; last_len = r; }   // cbits/lz4.c:2353-2355
-        }
-        if (st && last_out) {           // keep the reachable tail of the last output for the next call
-            uint32_t kept = last_len < 65536 ? (uint32_t)last_len : 65536u;
-            const uint8_t* from = last_out + last_len - kept;
-            uint8_t* to = st->tail + 65536 - kept;
             __syncwarp();
-            for (uint32_t i = lane; i < kept; i += 32) to[i] = from[i];
-            if (lane == 0) { st->prev_len = (uint32_t)last_len; st->kept = kept; }
+            // phase B: matches that read bytes of this batch, in order
+            uint32_t dep = __ballot_sync(kFull, has_match && !indep);
+            while (dep) {
+                const int l = __ffs(dep) - 1; dep &= dep - 1;
+                const int md = __shfl_sync(kFull, m_dst, l);
+                const uint32_t ml_ds = __shfl_sync(kFull, mlen | (dist << 16), l);
+                const uint32_t ml = ml_ds & 0xFFFFu, ds = ml_ds >> 16;
+                const int f0 = md - (int)ds;
+                // overlapping match (ds < ml <= 64): byte i comes from f0 + i mod ds; i mod ds through a 16-bit
+                // fixed-point reciprocal, exact for i < 64 (inv is 65536/ds plus at most 3)
+                const uint32_t inv = ds < ml ? (uint32_t)(65536.0f * __frcp_rn((float)ds)) + 2u : 0u;
+                #pragma unroll
+                for (uint32_t i0 = 0; i0 < kShortMatch; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    if (i < ml) {
+                        const int f = f0 + (int)(i - ((i * inv) >> 16) * ds);
+                        uint32_t bb;
+                        if (f >= ring_base) bb = lds8(C.oidx(f));
+                        else if (f >= 0) bb = dst[f];
+                        else bb = C.dict_end[f];
+                        sts8(C.oidx(md + (int)i), bb);
+                    }
+                    if (ml <= 32) break;
+                }
+                __syncwarp();
+            }
+            C.op = op1;
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q->empty[b]);
         }
-        __syncwarp();
+        batch++;
+
+        if (cf & kEndBlock) {
+            if (result >= 0 && dst) { C.flush(C.op, true); __syncwarp(); }
+            if (lane == 0) a.out_len[blk] = result;
+            if (result > 0) { C.dict_end = dst + result; C.dict_len = (uint32_t)result; last_out = dst; last_len = result; }   // cbits/lz4.c:2353-2355
+            if ((cf & kStreamEnd) && a.states && last_out) {   // keep the reachable tail of the last output for the next call
+                DState* st = reinterpret_cast<DState*>(a.states[stream]);
+                const uint32_t kept = last_len < 65536 ? (uint32_t)last_len : 65536u;
+                const uint8_t* fromp = last_out + last_len - kept;
+                uint8_t* to = st->tail + 65536 - kept;
+                __syncwarp();
+                for (uint32_t i = lane; i < kept; i += 32) to[i] = fromp[i];
+                if (lane == 0) { st->prev_len = (uint32_t)last_len; st->kept = kept; }
+            }
+            __syncwarp();
+        }
     }
+}
+
+__global__ void __launch_bounds__(64, 16)
+decompress_kernel(DecompressArgs a)
+{
+    __shared__ __align__(16) uint8_t in_ring[kInRing];
+    __shared__ __align__(16) uint8_t out_ring[kOutRing];
+    __shared__ DQueue queue;
+    if (threadIdx.x == 0) {
+        mbar_init(&queue.full[0], 1); mbar_init(&queue.full[1], 1);
+        mbar_init(&queue.empty[0], 1); mbar_init(&queue.empty[1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) parser_main(a, &queue, smem_u32(in_ring));
+    else copier_main(a, &queue, smem_u32(in_ring), smem_u32(out_ring));
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t done = atomicAdd(&a.scratch->work_counter[3], 1u);
@@ -292,10 +637,9 @@ cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream)
         e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
     }
     if (a.n_streams <= 0) return cudaSuccess;
-    int max_ctas = sm_count * 16;
-    int want = (a.n_streams + kDecWarps - 1) / kDecWarps;
-    int grid = want < max_ctas ? want : max_ctas;
-    decompress_kernel<<<grid, kDecWarps * 32, 0, stream>>>(a);
+    const int max_ctas = sm_count * 16;
+    const int grid = a.n_streams < max_ctas ? a.n_streams : max_ctas;
+    decompress_kernel<<<grid, 64, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
