@@ -51,7 +51,8 @@ constexpr int kEndBlock = 1 << 30;       // block finished; result[] holds what 
 constexpr int kTerminate = 1 << 29;
 
 struct __align__(16) DQueue {
-    uint4 desc[2][kQDepth];              // {literal start (ring space), literal length, match length (0 = none), offset}
+    uint4 desc[2][kQDepth];              // short: {literal start (ring space), lit | mlen << 8 | offset << 16, output position, -}
+                                         // bulk:  {literal start (ring space), literal length, match length (0 = none), offset}
     unsigned long long full[2], empty[2];
     int count[2];
     int block[2];
@@ -260,7 +261,7 @@ __device__ int parse_block(Parser& P, int skew, int src_len, int cap, uint32_t d
                 const bool bad = mine && (dist == 0u || (check_offset && (uint32_t)my_op + lit + dict_len < dist));
                 if (__ballot_sync(kFull, bad)) return -1;
                 const uint32_t rank = __popc(real & lanemask_lt());
-                if (mine) sts128(P.slot_s + 16u * rank, (uint32_t)p + 1u, lit, mlen, dist);
+                if (mine) sts128(P.slot_s + 16u * rank, (uint32_t)p + 1u, lit | (mlen << 8) | (dist << 16), (uint32_t)my_op, 0u);
                 const int n = __popc(real);
                 P.slot_s += 16u * (uint32_t)n; P.fill += n;
                 op = opr; ip += (int)cur;
@@ -296,7 +297,7 @@ __device__ int parse_block(Parser& P, int skew, int src_len, int cap, uint32_t d
         if (last) {
             if (len) {
                 if (bulk_lit) { if (P.fill) P.publish(0, 0, ip); P.push((uint32_t)ip, len, 0u, 0u); P.publish(kBulk, 0, ip + (int)len); }
-                else { P.ensure(ip, ip + (int)len); P.push((uint32_t)ip, len, 0u, 0u); }
+                else { P.ensure(ip, ip + (int)len); P.push((uint32_t)ip, len, (uint32_t)op, 0u); }
             }
             return op + (int)len;
         }
@@ -325,6 +326,7 @@ __device__ int parse_block(Parser& P, int skew, int src_len, int cap, uint32_t d
             }
         }
         mlen += kMinMatch;
+        const int op_seq = op;
         op += (int)len;
         const int from = op - (int)dist;
         if (check_offset && (long long)from + (long long)dict_len < 0) return -1;        // :2073
@@ -335,7 +337,7 @@ __device__ int parse_block(Parser& P, int skew, int src_len, int cap, uint32_t d
             P.push((uint32_t)lit_src, len, mlen, dist);
             P.publish(kBulk, 0, ip);
         } else {
-            P.push((uint32_t)lit_src, len, mlen, dist);
+            P.push((uint32_t)lit_src, len | (mlen << 8) | (dist << 16), (uint32_t)op_seq, 0u);
         }
         op += (int)mlen;
     }
@@ -424,6 +426,21 @@ struct Copier {
 
     __device__ __forceinline__ uint32_t oidx(int q) const { return out_s + (((uint32_t)q + oskew) & (kOutRing - 1)); }
 
+    // Make the ring hold the 64 output positions below `upto` (taken from global memory / the previous output),
+    // so that a short match that reaches back across a block start or a bulk copy still reads the ring.
+    __device__ void preload(int upto)
+    {
+        const uint32_t lane = lane_id();
+        #pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int qd = upto - 64 + (int)lane + 32 * k;
+            uint32_t bb = 0;
+            if (qd >= 0) bb = dst[qd];
+            else if ((uint32_t)(-qd) <= dict_len && (uint32_t)(-qd) <= 65536u) bb = dict_end[qd];
+            sts8(oidx(qd), bb);
+        }
+        ring_lo = upto - 64;
+    }
     // ring -> global for output positions [flushed, upto); unless `all`, stops at the last 16-byte boundary
     __device__ void flush(int upto, bool all)
     {
@@ -475,6 +492,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
                 C.dict_end = nullptr; C.dict_len = 0; last_out = nullptr; last_len = 0;
                 if (st && st->prev_len) { C.dict_len = st->prev_len; C.dict_end = st->tail + 65536; }
             }
+            if (C.dict_len) { C.preload(0); __syncwarp(); }
         }
         const int result = q->result[b];
         const int stream = q->stream[b];
@@ -522,65 +540,80 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
                 op += (int)mlen;
             }
             __syncwarp();
-            C.op = op; C.flushed = op; C.ring_lo = op;
+            C.op = op; C.flushed = op;
+            C.preload(op);
+            __syncwarp();
         } else if (cnt) {
             // ---- up to 32 short sequences
-            const uint32_t lit = d.y, mlen = d.z, dist = d.w;
-            const uint32_t tot = lit + mlen;
-            uint32_t incl = tot;
-            #pragma unroll
-            for (int dl = 1; dl < 32; dl <<= 1) { uint32_t v = __shfl_up_sync(kFull, incl, dl); if ((int)lane >= dl) incl += v; }
+            constexpr uint32_t M = kOutRing - 1;
+            const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
+            const int lit_dst = (int)d.z;
             const int op0 = C.op;
-            const int op1 = op0 + (int)__shfl_sync(kFull, incl, 31);
-            const int lit_dst = op0 + (int)(incl - tot);
+            const int op1 = __shfl_sync(kFull, lit_dst + (int)(lit + mlen), cnt - 1);
             const int m_dst = lit_dst + (int)lit;
             const int from = m_dst - (int)dist;
             C.flush(op0, false);                       // previous batches leave for global memory (128-bit stores)
             const int ring_base = max(C.ring_lo, op1 - kOutRing);       // output positions >= this are in the ring; below: in global memory
+            const uint32_t oskew = C.oskew;
             // phase A: literals (lane per sequence)
-            for (uint32_t i = 0; i < lit; i++)
-                sts8(C.oidx(lit_dst + (int)i), lds8(in_s + ((d.x + i) & (kInRing - 1))));
+            {
+                const uint32_t sl = d.x, dl = (uint32_t)lit_dst + oskew;
+                for (uint32_t i = 0; i < lit; i++) sts8(out_s + ((dl + i) & M), lds8(in_s + ((sl + i) & (kInRing - 1))));
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&q->empty[b]);  // descriptors are in registers and the input ring is no longer needed
             // phase A: matches whose source was complete before this batch
             const bool has_match = mlen != 0;
             const bool indep = has_match && (from + (int)mlen <= op0);
+            const uint32_t sa = (uint32_t)from + oskew, da = (uint32_t)m_dst + oskew;     // ring-space source / destination
             if (indep) {
-                for (uint32_t i = 0; i < mlen; i++) {
-                    const int f = from + (int)i;
-                    uint32_t bb;
-                    if (f >= ring_base) bb = lds8(C.oidx(f));
-                    else if (f >= 0) bb = dst[f];
-                    else bb = C.dict_end[f];
-                    sts8(C.oidx(m_dst + (int)i), bb);
+                if (from >= ring_base) {                                // source in the ring
+                    for (uint32_t i = 0; i < mlen; i++) sts8(out_s + ((da + i) & M), lds8(out_s + ((sa + i) & M)));
+                } else if (from >= 0) {                                 // source already flushed (from + mlen <= flushed)
+                    const uint8_t* g = dst + from;
+                    for (uint32_t i = 0; i < mlen; i++) sts8(out_s + ((da + i) & M), (uint32_t)g[i]);
+                } else {                                                // starts in the previous output (:2075-2100)
+                    for (uint32_t i = 0; i < mlen; i++) {
+                        const int f = from + (int)i;
+                        uint32_t bb;
+                        if (f < 0) bb = C.dict_end[f];
+                        else if (f >= ring_base) bb = lds8(out_s + ((sa + i) & M));
+                        else bb = dst[f];
+                        sts8(out_s + ((da + i) & M), bb);
+                    }
                 }
             }
             __syncwarp();
-            // phase B: matches that read bytes of this batch, in order
+            // phase B: matches that read bytes of this batch, in order, each copied by all lanes.  Their sources lie
+            // within 64 bytes of the batch start, which the ring always holds (see preload()).
             uint32_t dep = __ballot_sync(kFull, has_match && !indep);
-            while (dep) {
-                const int l = __ffs(dep) - 1; dep &= dep - 1;
-                const int md = __shfl_sync(kFull, m_dst, l);
-                const uint32_t ml_ds = __shfl_sync(kFull, mlen | (dist << 16), l);
-                const uint32_t ml = ml_ds & 0xFFFFu, ds = ml_ds >> 16;
-                const int f0 = md - (int)ds;
-                // overlapping match (ds < ml <= 64): byte i comes from f0 + i mod ds; i mod ds through a 16-bit
-                // fixed-point reciprocal, exact for i < 64 (inv is 65536/ds plus at most 3)
-                const uint32_t inv = ds < ml ? (uint32_t)(65536.0f * __frcp_rn((float)ds)) + 2u : 0u;
-                #pragma unroll
-                for (uint32_t i0 = 0; i0 < kShortMatch; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    if (i < ml) {
-                        const int f = f0 + (int)(i - ((i * inv) >> 16) * ds);
-                        uint32_t bb;
-                        if (f >= ring_base) bb = lds8(C.oidx(f));
-                        else if (f >= 0) bb = dst[f];
-                        else bb = C.dict_end[f];
-                        sts8(C.oidx(md + (int)i), bb);
+            if (dep) {
+                const uint32_t mlds = mlen | (dist << 16);
+                int l = __ffs(dep) - 1;
+                uint32_t n_da = __shfl_sync(kFull, da, l), n_mlds = __shfl_sync(kFull, mlds, l);
+                for (;;) {
+                    dep &= dep - 1;
+                    const uint32_t cda = n_da, ml = n_mlds & 0xFFFFu, ds = n_mlds >> 16;
+                    if (dep) {      // the next match's parameters travel while this one is copied
+                        l = __ffs(dep) - 1;
+                        n_da = __shfl_sync(kFull, da, l); n_mlds = __shfl_sync(kFull, mlds, l);
                     }
-                    if (ml <= 32) break;
+                    const uint32_t csa = cda - ds;
+                    if (ds >= ml) {
+                        if (lane < ml) sts8(out_s + ((cda + lane) & M), lds8(out_s + ((csa + lane) & M)));
+                        if (lane + 32 < ml) sts8(out_s + ((cda + lane + 32) & M), lds8(out_s + ((csa + lane + 32) & M)));
+                    } else {
+                        // overlapping match (ds < ml <= 64): byte i comes from source byte i mod ds; i mod ds through a
+                        // 16-bit fixed-point reciprocal, exact for i < 64 (inv is 65536/ds plus at most 3)
+                        const uint32_t inv = (uint32_t)(65536.0f * __frcp_rn((float)ds)) + 2u;
+                        const uint32_t i1 = lane + 32;
+                        const uint32_t k0 = lane - ((lane * inv) >> 16) * ds, k1 = i1 - ((i1 * inv) >> 16) * ds;
+                        if (lane < ml) sts8(out_s + ((cda + lane) & M), lds8(out_s + ((csa + k0) & M)));
+                        if (i1 < ml) sts8(out_s + ((cda + i1) & M), lds8(out_s + ((csa + k1) & M)));
+                    }
+                    __syncwarp();
+                    if (!dep) break;
                 }
-                __syncwarp();
             }
             C.op = op1;
         } else {
@@ -618,8 +651,11 @@ decompress_kernel(DecompressArgs a)
         mbar_init(&queue.empty[0], 1); mbar_init(&queue.empty[1], 1);
     }
     __syncthreads();
-    if (threadIdx.x < 32) parser_main(a, &queue, smem_u32(in_ring));
-    else copier_main(a, &queue, smem_u32(in_ring), smem_u32(out_ring));
+    uint32_t in_s, out_s;       // laundered so that the compiler keeps them in registers instead of re-deriving them in the hot loops
+    asm volatile("mov.u32 %0, %1;" : "=r"(in_s) : "r"(smem_u32(in_ring)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(out_s) : "r"(smem_u32(out_ring)));
+    if (threadIdx.x < 32) parser_main(a, &queue, in_s);
+    else copier_main(a, &queue, in_s, out_s);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t done = atomicAdd(&a.scratch->work_counter[3], 1u);
