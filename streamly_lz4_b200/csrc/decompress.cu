@@ -570,8 +570,22 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
                 if (from >= ring_base) {                                // source in the ring
                     for (uint32_t i = 0; i < mlen; i++) sts8(out_s + ((da + i) & M), lds8(out_s + ((sa + i) & M)));
                 } else if (from >= 0) {                                 // source already flushed (from + mlen <= flushed)
-                    const uint8_t* g = dst + from;
-                    for (uint32_t i = 0; i < mlen; i++) sts8(out_s + ((da + i) & M), (uint32_t)g[i]);
+                    // aligned 32-bit loads, four bytes per round trip (never touches a word that holds no source byte)
+                    const uintptr_t ga = reinterpret_cast<uintptr_t>(dst + from);
+                    const uint32_t* gw = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
+                    const uint32_t sh = (uint32_t)(ga & 3) * 8;
+                    const uint32_t nwords = ((uint32_t)(ga & 3) + mlen + 3) >> 2;
+                    uint32_t w0 = gw[0];
+                    for (uint32_t i = 0, k = 1; i < mlen; i += 4, k++) {
+                        const uint32_t w1 = k < nwords ? gw[k] : 0u;
+                        const uint32_t v = __funnelshift_r(w0, w1, sh);
+                        w0 = w1;
+                        const uint32_t n = min(4u, mlen - i);
+                        sts8(out_s + ((da + i) & M), v & 0xFFu);
+                        if (n > 1) sts8(out_s + ((da + i + 1) & M), (v >> 8) & 0xFFu);
+                        if (n > 2) sts8(out_s + ((da + i + 2) & M), (v >> 16) & 0xFFu);
+                        if (n > 3) sts8(out_s + ((da + i + 3) & M), v >> 24);
+                    }
                 } else {                                                // starts in the previous output (:2075-2100)
                     for (uint32_t i = 0; i < mlen; i++) {
                         const int f = from + (int)i;
