@@ -165,6 +165,7 @@ __device__ __forceinline__ void cp_async_4(uint32_t smem_addr, const void* g)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
@@ -196,7 +197,7 @@ struct Producer {
     }
     __device__ __forceinline__ void push(uint32_t lit_pos, uint32_t lit_len, uint32_t mcode, uint32_t off, int block)
     {
-        if (lane_id() == 0) sts128(slot_s, lit_pos, lit_len, mcode, off);
+        sts128(slot_s, lit_pos, lit_len, mcode, off);     // all lanes store the same 16 bytes: no lane predicate on the hot path
         slot_s += 16;
         if (++fill == kQueueDepth) flush(block, 0);
     }
@@ -301,17 +302,10 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
         // verify+count).  kRetest: the post-match probe, which first inserts p-2 and has no literals.
         // On a hit fills mip / mlen / dist and returns true.
         int mip = 0; uint32_t mlen = 0, dist = 0;
-        auto scalar_probe = [&](int p, bool retest) -> bool {
-            if (p >= trigger) move_window(p);
-            const uint32_t ap = g32 + (uint32_t)p;
-            const uint32_t mine = ring32(glane + (uint32_t)p);      // lane's 4 bytes of p.. (issued early: overlaps the table chain)
-            const uint32_t h = hash_at(ap);
+        // verify candidate index m for position p and count the match (table already updated)
+        auto verify_count = [&](int p, uint32_t m, bool retest) -> bool {
             const uint32_t cur = S + (uint32_t)p;
-            // every lane performs the same accesses in program order: no warp sync needed
-            if (retest) sts32(table_s + hash_at(ap - 2) * 4, cur - 2);                             // :1146
-            const uint32_t m = lds32(table_s + h * 4);
-            sts32(table_s + h * 4, cur);                                                             // :998 / :1185
-            if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) return false;             // :1001-1006 / :1187-1188
+            const uint32_t mine = ring32(glane + (uint32_t)p);      // lane's 4 bytes of p..
             uint32_t cap = (uint32_t)(mlimit - p);
             uint32_t L;
             const uint8_t* cand;
@@ -345,6 +339,49 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
             mip = p - (int)back; mlen = L + back; dist = cur - m;
             return true;
         };
+        auto scalar_probe = [&](int p, bool retest) -> bool {
+            if (p >= trigger) move_window(p);
+            const uint32_t ap = g32 + (uint32_t)p;
+            const uint32_t h = hash_at(ap);
+            const uint32_t cur = S + (uint32_t)p;
+            // every lane performs the same accesses in program order: no warp sync needed
+            if (retest) sts32(table_s + hash_at(ap - 2) * 4, cur - 2);                             // :1146
+            const uint32_t m = lds32(table_s + h * 4);
+            sts32(table_s + h * 4, cur);                                                             // :998 / :1185
+            if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) return false;             // :1001-1006 / :1187-1188
+            return verify_count(p, m, retest);
+        };
+
+        // The post-match probe (put(ip-2), re-test ip; cbits/lz4.c:1146, :1159-1196), the hot loop on compressible data.
+        // Lane l compares BYTE p+l with byte cand+l, so the match length is one ballot away (no per-lane
+        // word assembly, no shuffle); only matches of 32 bytes and more take a second, word-granular step.
+        auto retest_probe = [&](int p) -> bool {
+            if (p >= trigger) move_window(p);
+            const uint32_t ap = g32 + (uint32_t)p;
+            const uint32_t capb = min((uint32_t)(mlimit - p), 32u);
+            const uint32_t mine = lds8(and_or(ap + lane, kWinBytes - 1, data_s));     // issued early: overlaps the table chain
+            const uint32_t h = hash_at(ap);
+            const uint32_t cur = S + (uint32_t)p;
+            sts32(table_s + hash_at(ap - 2) * 4, cur - 2);                                           // :1146
+            const uint32_t m = lds32(table_s + h * 4);
+            sts32(table_s + h * 4, cur);                                                             // :1185
+            if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) return false;             // :1187-1188
+            if (m < S) return verify_count(p, m, true);                                              // candidate in the dictionary
+            const int cpos = (int)(m - S);
+            uint32_t theirs = 0x100u;                           // lanes past the cap differ by construction
+            if (lane < capb)
+                theirs = (cpos >= lo_pos) ? lds8(and_or(g32 + (uint32_t)cpos + lane, kWinBytes - 1, data_s)) : (uint32_t)__ldg(src + cpos + lane);
+            const uint32_t ne = __ballot_sync(kFull, mine != theirs);
+            uint32_t L;
+            if (ne) L = (uint32_t)__ffs(ne) - 1u;
+            else {                                              // 32 equal bytes and room for more
+                const uint32_t cap = (uint32_t)(mlimit - p);
+                L = 32u + (cap > 32u ? warp_common_prefix(src + p + 32, src + cpos + 32, cap - 32u) : 0u);
+            }
+            if (L < 4) return false;                                                                 // :1189
+            mip = p; mlen = L; dist = cur - m;
+            return true;
+        };
 
         if (lane == 0) { uint2 v = ldg_5bytes(src); table[hash5(v.x, v.y)] = S; }   // :924
         __syncwarp();
@@ -357,7 +394,7 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
             if (after_match) {
                 // ---- put(ip-2), re-test ip (cbits/lz4.c:1146, :1159-1196); ip == anchor here.
                 // Loops for as long as a match immediately follows a match.
-                while (scalar_probe(ip, true)) {
+                while (retest_probe(ip)) {
                     out.push((uint32_t)ip, 0u, mlen - 4, dist, in.block);
                     ip += (int)mlen;
                     anchor = ip;
@@ -625,7 +662,7 @@ __device__ void emitter_main(const CompressArgs& a, Queue* q)
     }
 }
 
-__global__ void __launch_bounds__(kPairs * 64)
+__global__ void __launch_bounds__(kPairs * 64, 3)
 compress_kernel(CompressArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_dyn[];
