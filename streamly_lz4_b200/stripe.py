@@ -1,0 +1,66 @@
+"""Striping of blocks / streams over the GPUs of one box.
+
+The codec path has no exchange step: independent blocks shard by contiguous block
+range, linked streams shard by whole streams, results are concatenated in block
+order.  The only communication is bookkeeping (per-block output lengths, so that
+every rank -- or just rank 0 -- knows where each block lands in the global output
+stream); it runs over whatever torch.distributed backend the launcher initialised
+(NCCL on the GPU box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def stripe_range(n_units: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous range [lo, hi) of unit indices owned by `rank`; sizes differ by at most one."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("rank/world")
+    q, r = divmod(max(n_units, 0), world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def stripe_streams(stream_first: Optional[np.ndarray], n_blocks: int, rank: int, world: int):
+    """Shard whole streams.  Returns (block_lo, block_hi, local_stream_first or None).
+
+    stream_first None means independent blocks (every block its own unit)."""
+    if stream_first is None:
+        lo, hi = stripe_range(n_blocks, rank, world)
+        return lo, hi, None
+    sf = np.asarray(stream_first, dtype=np.int64)
+    s_lo, s_hi = stripe_range(len(sf) - 1, rank, world)
+    b_lo, b_hi = int(sf[s_lo]), int(sf[s_hi])
+    return b_lo, b_hi, (sf[s_lo:s_hi + 1] - b_lo).astype(np.int32)
+
+
+def gather_lengths(local_lens: np.ndarray, n_total: int, rank: int, world: int, device=None) -> np.ndarray:
+    """All ranks' per-block output lengths in global block order (int32[n_total]).
+
+    Stripes are the contiguous ranges of stripe_range(), so a padded all_gather is enough."""
+    local = np.ascontiguousarray(local_lens, dtype=np.int32)
+    if world == 1:
+        return local.copy()
+    import torch
+    import torch.distributed as dist
+    width = max(stripe_range(n_total, r, world)[1] - stripe_range(n_total, r, world)[0] for r in range(world))
+    t = torch.zeros(width, dtype=torch.int32, device=device)
+    t[:len(local)] = torch.from_numpy(local).to(t.device)
+    parts = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    out = np.zeros(n_total, dtype=np.int32)
+    for r, p in enumerate(parts):
+        lo, hi = stripe_range(n_total, r, world)
+        out[lo:hi] = p[:hi - lo].cpu().numpy()
+    return out
+
+
+def global_offsets(all_lens: np.ndarray, header: int) -> np.ndarray:
+    """Start of every framed block in the concatenated output stream (int64[n + 1]);
+    failed blocks (len <= 0) occupy nothing, as in b200lz4_compact_dev."""
+    sizes = np.where(all_lens > 0, all_lens.astype(np.int64) + header, 0)
+    off = np.zeros(len(all_lens) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=off[1:])
+    return off

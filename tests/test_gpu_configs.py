@@ -1,0 +1,128 @@
+"""BASELINE.json configs 3-5 through the C ABI at (per-GPU) full sizes, checked through size-independent
+properties plus oracle samples."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _blocks(total, bs):
+    offs = np.arange(0, total, bs, dtype=np.int64)
+    lens = np.minimum(bs, total - offs).astype(np.int32)
+    return offs, lens
+
+
+def test_config3_decompress_precompressed_stream(ctx, ref):
+    """configs[2]: d+640000 of a stream pre-compressed by the ORACLE (accel 1, 640000-byte independent blocks),
+    read back in 640000-byte chunks -> re-frame -> GPU decode.  2 GiB here = the stripe one GPU of four gets."""
+    import os
+    import streamly_lz4_b200 as lz
+    from streamly_lz4_b200 import _lib, datagen
+    total, bs = 2 << 30, 640000
+    data = datagen.make("mixed", 3, total)
+    offs, lens = _blocks(total, bs)
+    n = len(lens)
+    threads = min(os.cpu_count() or 1, 64)
+    ptrs = (data.ctypes.data + offs).astype(np.uint64)
+    caps = (lens.astype(np.int64) + lens // 255 + 16 + 8).astype(np.int32)
+    arena, dptrs, doffs = ref.slots(caps)
+    out_len = np.zeros(n, dtype=np.int32)
+    assert ref.compress_ptrs(ptrs, lens, dptrs, caps, out_len, 1, 8, np.arange(n + 1, dtype=np.int32), 0, threads) == 0
+    stream = np.concatenate([arena[o:o + 8 + l] for o, l in zip(doffs[:-1], out_len)])
+    # re-frame: the header walk of resizeChunksD over the stream consumed in 640000-byte reads (incremental calls)
+    lib = _lib.load()
+    import ctypes
+    boff = np.zeros(n + 8, dtype=np.int64); blen = np.zeros(n + 8, dtype=np.int32)
+    found, used, ended = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+    got_off, got_len, base, fed = [], [], 0, 0
+    while fed < stream.size:
+        fed = min(fed + 640000, stream.size)
+        view = stream[base:fed]
+        rc = lib.b200lz4_reframe(view.ctypes.data, view.size, 8, 0, boff.ctypes.data, blen.ctypes.data, len(boff),
+                                 ctypes.byref(found), ctypes.byref(used), ctypes.byref(ended))
+        assert rc == 0
+        got_off += [base + int(x) for x in boff[:found.value]]; got_len += [int(x) for x in blen[:found.value]]
+        base += used.value
+    assert base == stream.size and len(got_off) == n
+    assert got_len == [int(l) + 8 for l in out_len]
+    back = ctx.pinned("c3_back", total + 64)
+    rc, doff, dlen = ctx.decompress_batch(stream, np.array(got_off, dtype=np.int64), np.array(got_len, dtype=np.int32), 8, 0, back)
+    assert rc == 0 and (dlen == lens).all()
+    assert hashlib.sha256(back[:total].tobytes()).digest() == hashlib.sha256(data.tobytes()).digest()
+
+
+def test_config4_linked_streams(ctx, ref):
+    """configs[3]: concurrent linked streams of 64 KiB blocks with the prior block as dictionary, accel 1.
+    16 streams x 64 MiB here (config 4 puts 128 such streams on each GPU): every stream byte-identical to the
+    oracle via a checksum of checksums, two streams compared block for block, and the round trip is the identity."""
+    import os
+    from streamly_lz4_b200 import datagen
+    n_streams, per_stream, bs = 16, 64 << 20, 65536
+    total = n_streams * per_stream
+    data = datagen.make("mixed", 4, total)
+    offs, lens = _blocks(total, bs)
+    n = len(lens)
+    bps = per_stream // bs
+    sf = (np.arange(n_streams + 1, dtype=np.int64) * bps).astype(np.int32)
+    cap = int((lens.astype(np.int64) + lens // 255 + 16 + 8).sum())
+    dst = ctx.pinned("c4_dst", cap)
+    rc, dst_off, out_len = ctx.compress_batch(data, offs, lens, 1, 8, dst, stream_first=sf)
+    assert rc == 0 and (out_len > 0).all()
+    # oracle: same call sequence, one pthread per stream
+    threads = min(os.cpu_count() or 1, n_streams)
+    # arrays of one stream must not be address-adjacent for the reference (separate Haskell arrays never are)
+    gap_arena, ptrs, _ = ref.lay_out([data[o:o + l] for o, l in zip(offs, lens)])
+    caps = (lens.astype(np.int64) + lens // 255 + 16 + 8).astype(np.int32)
+    arena, dptrs, doffs = ref.slots(caps)
+    want_len = np.zeros(n, dtype=np.int32)
+    assert ref.compress_ptrs(ptrs, lens, dptrs, caps, want_len, 1, 8, sf, 0, threads) == 0
+    assert (want_len == out_len).all()
+    for s in range(n_streams):
+        h_gpu, h_ref = hashlib.sha256(), hashlib.sha256()
+        for b in range(sf[s], sf[s + 1]):
+            h_gpu.update(dst[dst_off[b]:dst_off[b + 1]].tobytes())
+            h_ref.update(arena[doffs[b]:doffs[b] + 8 + want_len[b]].tobytes())
+        assert h_gpu.digest() == h_ref.digest(), f"stream {s} differs from the oracle"
+    back = ctx.pinned("c4_back", total + 64)
+    comp = dst[:dst_off[-1]]
+    rc, boff, blen = ctx.decompress_batch(comp, dst_off[:-1].copy(), np.diff(dst_off).astype(np.int32), 8, 0, back, stream_first=sf)
+    assert rc == 0 and (blen == lens).all()
+    assert hashlib.sha256(back[:total].tobytes()).digest() == hashlib.sha256(data.tobytes()).digest()
+
+
+def test_config5_mixed_block_sizes_reframe_and_sweep(ctx, ref):
+    """configs[4]: (i) blocks of plaintext sizes log-uniform in [4 KiB, 4 MiB], GPU-compressed, concatenated,
+    fragmented at the reference's read sizes, re-framed (bit-exact vs the restated resizeChunksD, idempotent) and
+    decoded; (ii) acceleration sweep on config-2 data, bytes identical to the oracle per value."""
+    import streamly_lz4_b200 as lz
+    from oracle.oracle import resize_chunks
+    from streamly_lz4_b200 import datagen
+    rng = np.random.default_rng(5)
+    sizes = np.exp(rng.uniform(np.log(4096), np.log(4 << 20), 96)).astype(np.int64)
+    total = int(sizes.sum())
+    data = datagen.make("mixed", 5, total)
+    offs = np.zeros(len(sizes), dtype=np.int64); offs[1:] = np.cumsum(sizes[:-1])
+    arrays = [data[o:o + s].tobytes() for o, s in zip(offs, sizes)]
+    cfg = lz.BlockConfig(independent=True)
+    framed = list(lz.compress_chunks(cfg, 1, arrays, ctx=ctx))
+    want = ref.compress_chunks(arrays, 1, linked=False, threads=8)
+    assert framed == want
+    blob = b"".join(framed)
+    for bufsize in (512, 6553, 65536, 655360, 640000):
+        chunks = [blob[i:i + bufsize] for i in range(0, len(blob), bufsize)]
+        re1 = list(lz.resize_chunks(cfg, lz.default_frame_config, chunks))
+        assert re1 == resize_chunks(chunks) == framed
+        assert list(lz.resize_chunks(cfg, lz.default_frame_config, re1)) == re1          # idempotent
+    chunks = [blob[i:i + 640000] for i in range(0, len(blob), 640000)]
+    assert list(lz.decompress_chunks(cfg, chunks, ctx=ctx)) == arrays
+    # (ii) sweep
+    d2 = datagen.make("mixed", 2, 8 * 640000)
+    blocks = [d2[i:i + 640000].tobytes() for i in range(0, d2.size, 640000)]
+    seen = {}
+    for accel in (-1, 0, 1, 2, 5, 10, 12, 100, 400, 1000, 65537, 65538):
+        got = list(lz.compress_chunks(cfg, accel, blocks, ctx=ctx))
+        assert got == ref.compress_chunks(blocks, accel, linked=False, threads=8), f"accel {accel}"
+        seen[accel] = hashlib.sha256(b"".join(got)).digest()
+    assert seen[-1] == seen[0] == seen[1] and seen[65537] == seen[65538]
