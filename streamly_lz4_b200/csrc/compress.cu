@@ -389,6 +389,7 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
         bool after_match = false;
         bool narrow = false;                   // adaptive probe-window width
         bool first_scalar = false;             // predictor: the previous run hit on its first probe
+        const bool ring_probes = in.accel <= 8; // the first probes of a run are (nearly) consecutive positions
         for (;;) {
             bool have = false;
             if (after_match) {
@@ -404,6 +405,7 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
             }
             if ((uint32_t)ip + kPrefetchAhead > pf_next) l2_prefetch(ip);
             // ---- a search run starts at ip (cbits/lz4.c:956-1014)
+            if (ring_probes && ip >= trigger) move_window(ip);      // dense probing: keep the rings under the first window
             long long jbase = 0;
             if (first_scalar) {                // probe 0 of the run on the scalar path
                 if (ip + 1 > mfl) break;                                                             // :969
@@ -426,8 +428,13 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
                     uint32_t h = 0, seq = 0, cur = 0;
                     const int pos = valid ? (int)pos64 : 0;
                     if (valid) {
-                        uint2 v = ldg_5bytes(src + pos);
-                        seq = v.x; h = hash5(v.x, v.y); cur = S + (uint32_t)pos;
+                        cur = S + (uint32_t)pos;
+                        if (pos >= lo_pos && pos + 8 <= ready_end) {    // bytes and hash are already in the rings
+                            seq = ring32(g32 + (uint32_t)pos); h = hash_at(g32 + (uint32_t)pos);
+                        } else {
+                            uint2 v = ldg_5bytes(src + pos);
+                            seq = v.x; h = hash5(v.x, v.y);
+                        }
                     }
                     const uint32_t peers = __match_any_sync(kFull, valid ? h : (0x1000u + lane));
                     const uint32_t lower = peers & lanemask_lt();
@@ -465,21 +472,22 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
                 first_scalar = (hit_index == 0);
 
                 // catch up (cbits/lz4.c:1019), then count (:1076-1095)
-                mip = mpos;
+                // The backward and the forward extension are independent: the byte pair that decides whether there
+                // is anything to catch up is requested before the forward count, so both round trips overlap.
                 const bool in_dict = midx < S;
                 const uint8_t* cand = in_dict ? (in.dict_end - (S - midx)) : (src + (midx - S));
-                {
-                    const uint32_t room_c = in_dict ? (in.dict_len - (S - midx)) : (midx - S);
-                    const uint32_t maxback = min((uint32_t)(mip - anchor), room_c);
-                    const uint32_t back = maxback ? warp_common_suffix(src + mip, cand, maxback) : 0u;
-                    mip -= (int)back; cand -= back;
-                }
-                uint32_t cap = (uint32_t)(mlimit - mip);
+                const uint32_t room_c = in_dict ? (in.dict_len - (S - midx)) : (midx - S);
+                const uint32_t maxback = min((uint32_t)(mpos - anchor), room_c);
+                uint32_t b_src = 0, b_cand = 1;
+                if (maxback) { b_src = __ldg(src + mpos - 1); b_cand = __ldg(cand - 1); }
+                uint32_t cap = (uint32_t)(mlimit - mpos);
                 if (in_dict) cap = min(cap, (uint32_t)(in.dict_end - cand));
-                uint32_t L = 4 + warp_common_prefix(src + mip + 4, cand + 4, cap - 4);
-                if (in_dict && L == cap && mip + (int)L < mlimit)
-                    L += warp_common_prefix(src + mip + L, src, (uint32_t)(mlimit - (mip + (int)L)));
-                mlen = L; dist = (S + (uint32_t)mpos) - midx;
+                uint32_t L = 4 + warp_common_prefix(src + mpos + 4, cand + 4, cap - 4);
+                if (in_dict && L == cap && mpos + (int)L < mlimit)
+                    L += warp_common_prefix(src + mpos + L, src, (uint32_t)(mlimit - (mpos + (int)L)));
+                const uint32_t back = (b_src == b_cand) ? warp_common_suffix(src + mpos, cand, maxback) : 0u;
+                mip = mpos - (int)back;
+                mlen = L + back; dist = (S + (uint32_t)mpos) - midx;
             }
             out.push((uint32_t)anchor, (uint32_t)(mip - anchor), mlen - 4, dist, in.block);
             ip = mip + (int)mlen;
