@@ -260,6 +260,7 @@ def run_gpu(args):
     e2e_t = []
     split = {"h2d_ms": [], "kernel_ms": [], "d2h_ms": []}
     barrier()
+    launches0 = ctx.launch_count()
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
         t1 = time.perf_counter()
@@ -270,7 +271,7 @@ def run_gpu(args):
             split[k].append(tm[k])
     barrier()
     e2e_wall = time.perf_counter() - t_all0
-    e2e_launches = args.steps * 3
+    e2e_launches = ctx.launch_count() - launches0          # counted by the library: chunks x (codec + scan + gather)
     assert rc == 0 and int(doff[-1]) == comp_total
     clocks = sampler.stop() if rank == 0 else None
 
@@ -311,6 +312,23 @@ def run_gpu(args):
         same = bool(torch.equal(d_back[:total], d_src)) and bool((d_back_len == d_src_len).all().item())
         extra["decompress"] = {"ms_per_step": d_ms, "round_trip_identical": same}
         gpu_launches_extra = args.steps
+        # the same through b200lz4_decompress_batch (pinned host in / out)
+        comp_host = pin_dst[:comp_total]
+        pin_back = ctx.pinned("b_back", total + 64)
+        c_off_h = np.ascontiguousarray(doff[:-1]); c_len_h = np.diff(doff).astype(np.int32)
+        for _ in range(2):
+            rc2, boff, blen = ctx.decompress_batch(comp_host, c_off_h, c_len_h, HEADER, 0, pin_back)
+            assert rc2 == 0, _lib.last_error()
+        barrier()
+        t_d0 = time.perf_counter()
+        for _ in range(args.steps):
+            rc2, boff, blen = ctx.decompress_batch(comp_host, c_off_h, c_len_h, HEADER, 0, pin_back)
+        barrier()
+        d_e2e = (time.perf_counter() - t_d0) / args.steps
+        tmd = ctx.timing()
+        extra["decompress"]["e2e"] = {"wall_ms_per_step": 1e3 * d_e2e, "h2d_ms": tmd["h2d_ms"], "kernel_ms": tmd["kernel_ms"],
+                                      "d2h_ms": tmd["d2h_ms"], "identical": bool((pin_back[:total] == host).all())}
+        gpu_launches_extra += ctx.launch_count() - launches0 - e2e_launches
 
     # ---- reduce over ranks (max time)
     def rmax(x):
@@ -328,6 +346,8 @@ def run_gpu(args):
     if "decompress" in extra:
         dms = rmax(extra["decompress"]["ms_per_step"])
         extra["decompress"].update({"ms_per_step": dms, "value": world * total / (dms / 1e3) / 1e9, "unit": UNIT})
+        de = rmax(extra["decompress"]["e2e"]["wall_ms_per_step"])
+        extra["decompress"]["e2e"].update({"wall_ms_per_step": de, "value": world * total / (de / 1e3) / 1e9, "unit": UNIT})
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -338,11 +358,13 @@ def run_gpu(args):
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo, "kernel_ms": k_ms, "compact_ms": statistics.mean(compact_ms),
                 "kernel_share_of_step": k_ms / ms_per_step}
+        traffic = {}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
                 if tj.get("size_mib") == args.size_mib:
+                    traffic = tj
                     roof["traffic"] = tj.get("compress_kernel_dram_bytes")
             except Exception:
                 pass
@@ -351,6 +373,7 @@ def run_gpu(args):
             dv["roofline"] = {"bound": "hbm", "kernel": "decompress_kernel",
                               "achieved": algo / (dv["ms_per_step"] / 1e3) / 1e9 * 1.0, "peak": peak, "unit": "GB/s"}
             dv["roofline"]["frac"] = dv["roofline"]["achieved"] / peak
+            dv["roofline"]["traffic"] = traffic.get("decompress_kernel_dram_bytes")
         cpu = None
         if not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -376,7 +399,7 @@ def run_gpu(args):
                     "d2h_ms": statistics.mean(split["d2h_ms"]), "wall_ms_per_step": 1e3 * e2e_wall / args.steps},
             "gpu_launches": gpu_launches + e2e_launches + (gpu_launches_extra if "decompress" in extra else 0),
             "gpu_launches_detail": {"timed_value_region": gpu_launches, "e2e_region": e2e_launches,
-                                    "per_step": "compress_kernel + scan_kernel + gather_kernel"},
+                                    "per_step": "compress_kernel + scan_kernel + gather_kernel (e2e: per pipeline chunk)"},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "parity": parity, "extra": extra,
         }
         print(json.dumps(line), flush=True)
