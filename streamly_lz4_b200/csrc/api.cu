@@ -55,8 +55,8 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 4096;
-        cudaError_t e = cudaMallocHost(&p, want);
-        if (e != cudaSuccess) { p = nullptr; return fail(B200LZ4_E_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable);    // device-visible: kernels mirror sizes into it
+        if (e != cudaSuccess) { p = nullptr; return fail(B200LZ4_E_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
         cap = want;
         return 0;
     }
@@ -287,13 +287,11 @@ int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
         a.accel = accel; a.header = header; a.scratch = c->scratch + k;
         CU(launch_compress(a, ks));
         const int nk = ch.b1 - ch.b0;
-        CompactArgs g{d_slots, a.dst_off + ch.b0, d_out_len + ch.b0, nk, header, d_out + h_slot_off[ch.b0], d_out_off + ch.b0 + k};
+        // the scan kernel mirrors sizes and offsets into the pinned descriptor block (device-visible host memory)
+        CompactArgs g{d_slots, a.dst_off + ch.b0, d_out_len + ch.b0, nk, header, d_out + h_slot_off[ch.b0], d_out_off + ch.b0 + k,
+                      reinterpret_cast<int64_t*>(hd + o_out_off) + ch.b0 + k, reinterpret_cast<int32_t*>(hd + o_out_len) + ch.b0};
         CU(launch_compact(g, ks));
         c->launches += kernel_launches_per_compress() + kernel_launches_per_compact();
-        CU(cudaMemcpyAsync(hd + o_out_len + sizeof(int32_t) * ch.b0, dd + o_out_len + sizeof(int32_t) * ch.b0,
-                           sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, ks));
-        CU(cudaMemcpyAsync(hd + o_out_off + sizeof(int64_t) * (ch.b0 + k), dd + o_out_off + sizeof(int64_t) * (ch.b0 + k),
-                           sizeof(int64_t) * (nk + 1), cudaMemcpyDeviceToHost, ks));
         if (k == nchunks - 1) CU(cudaEventRecord(c->ev[2], ks));
         CU(cudaEventRecord(c->ev_k[k], ks));
     }
@@ -325,6 +323,16 @@ int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&c->t_kernel, c->ev_k0, c->ev[2]);
     cudaEventElapsedTime(&c->t_d2h, c->ev_d0, c->ev_d1);
+    if (getenv("B200LZ4_DEBUG")) {          // device timeline of the pipeline, ms since the call's first event
+        float t = 0;
+        for (int k = 0; k < nchunks; k++) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, c->ev[0], c->ev_h2d[k]); cudaEventElapsedTime(&b, c->ev[0], c->ev_k[k]);
+            fprintf(stderr, "[b200lz4] chunk %d: blocks %d..%d  h2d done %.2f  kernels done %.2f\n", k, chunks[k].b0, chunks[k].b1, a, b);
+        }
+        cudaEventElapsedTime(&t, c->ev[0], c->ev_d1);
+        fprintf(stderr, "[b200lz4] d2h done %.2f\n", t);
+    }
     if (streams) for (int s = 0; s < n_streams; s++)
         if (stream_first[s + 1] > stream_first[s]) streams[s]->last_len = (uint32_t)src_len[stream_first[s + 1] - 1];
     for (int i = 0; i < n; i++) if (out_len[i] <= 0) return fail(B200LZ4_E_BLOCK, "block " + std::to_string(i) + " failed to compress");
@@ -430,7 +438,7 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
         c->launches += kernel_launches_per_decompress();
         const int nk = ch.b1 - ch.b0;
         if (!contiguous) {
-            CompactArgs g{d_slots, a.dst_off + ch.b0, d_out_len + ch.b0, nk, 0, d_out + h_slot_off[ch.b0], d_out_off + ch.b0 + k};
+            CompactArgs g{d_slots, a.dst_off + ch.b0, d_out_len + ch.b0, nk, 0, d_out + h_slot_off[ch.b0], d_out_off + ch.b0 + k, nullptr, nullptr};
             CU(launch_compact(g, ks));
             c->launches += kernel_launches_per_compact();
             CU(cudaMemcpyAsync(hd + o_out_off + sizeof(int64_t) * (ch.b0 + k), dd + o_out_off + sizeof(int64_t) * (ch.b0 + k),
@@ -523,8 +531,8 @@ int b200lz4_ctx_create(int device, b200lz4_ctx** out)
     if (e2 == cudaSuccess) e2 = cudaMemset(c->scratch, 0, sizeof(Scratch) * kMaxChunks);
     for (int i = 0; i < 4 && e2 == cudaSuccess; i++) e2 = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < kMaxChunks && e2 == cudaSuccess; i++) {
-        e2 = cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming);
-        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming);
+        e2 = cudaEventCreate(&c->ev_h2d[i]);
+        if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev_k[i]);
     }
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev_k0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev_d0);
@@ -700,7 +708,7 @@ int b200lz4_compact_dev(const void* d_slots, const int64_t* d_slot_off, const in
     (void)d_scratch;
     if (n_blocks < 0) return fail(B200LZ4_E_ARG, "bad argument");
     CompactArgs g{static_cast<const uint8_t*>(d_slots), d_slot_off, d_len, n_blocks, header_mode,
-                  static_cast<uint8_t*>(d_out), d_out_off};
+                  static_cast<uint8_t*>(d_out), d_out_off, nullptr, nullptr};
     CU(launch_compact(g, static_cast<cudaStream_t>(cuda_stream)));
     return 0;
 }

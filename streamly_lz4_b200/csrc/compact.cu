@@ -11,7 +11,8 @@ namespace {
 constexpr int kScanThreads = 1024;
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_kernel(const int32_t* __restrict__ len, int n, int header, int64_t* __restrict__ out_off)
+scan_kernel(const int32_t* __restrict__ len, int n, int header, int64_t* __restrict__ out_off,
+            int64_t* __restrict__ host_off, int32_t* __restrict__ host_len)
 {
     __shared__ long long partial[kScanThreads];
     const int t = threadIdx.x;
@@ -28,8 +29,13 @@ scan_kernel(const int32_t* __restrict__ len, int n, int header, int64_t* __restr
         __syncthreads();
     }
     long long run = partial[t] - sum;                   // exclusive prefix of this thread's chunk
-    for (int i = lo; i < hi; i++) { out_off[i] = run; int l = len[i]; run += (l > 0) ? (long long)(l + header) : 0; }
-    if (t == kScanThreads - 1) out_off[n] = partial[t];
+    for (int i = lo; i < hi; i++) {
+        const int l = len[i];
+        out_off[i] = run;
+        if (host_off) { host_off[i] = run; host_len[i] = l; }
+        run += (l > 0) ? (long long)(l + header) : 0;
+    }
+    if (t == kScanThreads - 1) { out_off[n] = partial[t]; if (host_off) host_off[n] = partial[t]; }
 }
 
 constexpr int kGatherThreads = 256;
@@ -83,7 +89,7 @@ cudaError_t launch_compact(const CompactArgs& a, cudaStream_t stream)
         int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
     }
-    scan_kernel<<<1, kScanThreads, 0, stream>>>(a.len, a.n_blocks, a.header, a.out_off);
+    scan_kernel<<<1, kScanThreads, 0, stream>>>(a.len, a.n_blocks, a.header, a.out_off, a.host_off, a.host_len);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || a.n_blocks <= 0) return e;
     int grid = a.n_blocks < sm_count * 8 ? a.n_blocks : sm_count * 8;

@@ -27,6 +27,9 @@ struct DecompressArgs {
 struct CompactArgs {
     const uint8_t* slots; const int64_t* slot_off; const int32_t* len; int n_blocks;
     int header; uint8_t* out; int64_t* out_off;
+    // optional mirrors in mapped pinned HOST memory (written by the scan kernel over PCIe, so the host learns the
+    // sizes without a D2H memcpy that would queue behind bulk transfers on the copy engine)
+    int64_t* host_off; int32_t* host_len;
 };
 
 cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream);
