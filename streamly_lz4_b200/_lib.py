@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200lz4.so")
+LIB_PATH = os.environ.get("B200LZ4_LIB") or os.path.join(_HERE, "libb200lz4.so")   # override: A/B builds of the same ABI
 
 c_int, c_i64, c_vp, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t
 
