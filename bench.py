@@ -170,6 +170,9 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback")
+    from streamly_lz4_b200 import stripe
+    numa = stripe.bind_host_to_device(local)               # pinned staging buffers next to this rank's GPU
+    log(f"[rank {rank}] host binding: {numa}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -391,7 +394,7 @@ def run_gpu(args):
             "config": {"workload": f"BASELINE configs[1]: {args.size_mib} MiB mixed-entropy stream per GPU, c+{ACCEL}+{BLOCK}, "
                                    f"independent blocks ({n} blocks/GPU), BlockHasSize headers; step = codec kernel + compaction",
                        "ratio": total / comp_total, "l2": "inputs_exceed_l2 (1 GiB in, 0.6+ GiB out per step)",
-                       "parallelism": f"block stripes over {world} GPU(s), no collective"},
+                       "parallelism": f"block stripes over {world} GPU(s), no collective", "host_numa": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total + 20 * n,
                     "d2h_bytes_per_step": comp_total + 12 * n + 8,
                     "api": "b200lz4_compress_batch (pinned host in/out)",

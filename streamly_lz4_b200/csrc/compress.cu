@@ -247,9 +247,9 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
         };
         auto hash_at = [&](uint32_t a) { return lds16(and_or(a << 1, 2 * kWinBytes - 2, hash_s)); };
         auto issue = [&](uintptr_t line) {     // one 4-byte cp.async per lane; lines outside the block are not touched
-            if ((line << 7) < end && ((line + 1) << 7) > base)
-                cp_async_4(data_s + (uint32_t)(((line & (kWinLines - 1)) * 32 + lane) * 4),
-                           reinterpret_cast<const void*>((line << 7) + 4 * lane));
+            const uintptr_t wa = (line << 7) + 4 * lane;       // this lane's aligned word: copied only if it holds a byte of the block
+            if (wa < end && wa + 4 > base)
+                cp_async_4(data_s + (uint32_t)(((line & (kWinLines - 1)) * 32 + lane) * 4), reinterpret_cast<const void*>(wa));
             cp_async_commit();
         };
         auto hash_round = [&](int p0) {        // hashes of the 128 positions from p0 on ((g32 + p0) % 4 == 0)

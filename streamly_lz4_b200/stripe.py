@@ -64,3 +64,41 @@ def global_offsets(all_lens: np.ndarray, header: int) -> np.ndarray:
     off = np.zeros(len(all_lens) + 1, dtype=np.int64)
     np.cumsum(sizes, out=off[1:])
     return off
+
+
+def bind_host_to_device(device: int) -> dict:
+    """Best effort: run this process on the CPUs of the NUMA node the GPU hangs off and prefer that node for new
+    pages, so that pinned staging buffers (allocated afterwards) are node-local and H2D / D2H copies do not cross
+    the socket interconnect.  One process per GPU calls this before allocating.  Returns what was done."""
+    import ctypes
+    import os
+    import subprocess
+    info = {"device": device, "node": None, "cpus": None, "mempolicy": None}
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return info
+        if len(bus.split(":")[0]) == 8:          # nvidia-smi prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        target = cpus & os.sched_getaffinity(0)
+        if target:
+            os.sched_setaffinity(0, target)
+            info["cpus"] = len(target)
+        # set_mempolicy(MPOL_PREFERRED, {node}): syscall 238 on x86-64, 237 on aarch64
+        nr = {"x86_64": 238, "aarch64": 237}.get(os.uname().machine)
+        if nr is not None:
+            mask = ctypes.c_ulong(1 << node)
+            rc = ctypes.CDLL(None, use_errno=True).syscall(nr, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+            info["mempolicy"] = "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
+    except Exception as e:                      # sysfs not visible, no nvidia-smi, ...: stay as we are
+        info["error"] = repr(e)
+    return info
