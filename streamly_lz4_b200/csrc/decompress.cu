@@ -510,14 +510,17 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
             int op = C.op + (int)lit;
             __syncwarp();
             if (mlen) {
-                const int from = op - (int)dist;
+                int from = op - (int)dist;
                 uint8_t* out = dst + op;
-                if (from < 0) {                                        // starts in the previous output (:2075-2100)
-                    for (uint32_t i0 = 0; i0 < mlen; i0 += 32) {
-                        const uint32_t i = i0 + lane;
-                        if (i < mlen) { const int f = from + (int)i; out[i] = (f < 0) ? C.dict_end[f] : dst[f]; }
-                        __syncwarp();
-                    }
+                uint32_t mrest = mlen;
+                if (from < 0) {                                        // starts in the previous output (:2075-2100):
+                    const uint32_t nd = min(mrest, (uint32_t)(-from)); // that part first, the rest is an ordinary match from position 0
+                    for (uint32_t i = lane; i < nd; i += 32) out[i] = C.dict_end[from + (int)i];
+                    __syncwarp();
+                    out += nd; from += (int)nd; mrest -= nd;
+                }
+                const uint32_t mlen = mrest;                           // (shadows: what is left to copy from this block's own output)
+                if (mlen == 0) {
                 } else if (dist >= mlen) {
                     warp_copy_rw(out, dst + from, mlen);
                 } else if (dist >= 32) {                               // overlapping: rounds of one period each
@@ -537,8 +540,8 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
                         k += adv; if (k >= dist) k -= dist;
                     }
                 }
-                op += (int)mlen;
             }
+            op += (int)mlen;
             __syncwarp();
             C.op = op; C.flushed = op;
             C.preload(op);

@@ -1,0 +1,95 @@
+"""Randomised parity: (i) hand-built LZ4 blocks that exercise decoder paths the encoder never produces
+(offsets 1..3, long overlapping matches, 255-runs in both length fields, literal runs around the 15/32 limits,
+matches reaching into the previous block), decoded by the GPU and by the oracle; (ii) random arrays / sizes /
+accelerations / linkage through the whole compress -> decompress path against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _emit_len(out, v):
+    v -= 15
+    while v >= 255:
+        out.append(255); v -= 255
+    out.append(v)
+
+
+def build_block(rng, target, dict_avail):
+    """A valid LZ4 block of about `target` output bytes; returns (payload bytes, plaintext length)."""
+    out = bytearray()
+    produced = 0
+    plain_src = rng.integers(0, 256, size=target + 4096, dtype=np.uint8).tobytes()
+    while True:
+        style = rng.integers(0, 8)
+        lit = int(rng.choice([0, 0, 1, 3, 14, 15, 16, 31, 32, 33, 60, 270, 600])) if style else int(rng.integers(0, 20))
+        if produced + lit + 40 >= target:
+            break
+        reach = produced + lit + dict_avail
+        if reach < 1:
+            lit = max(lit, 1); reach = produced + lit + dict_avail
+        off = int(rng.choice([1, 2, 3, 4, 7, 8, 15, 16, 31, 32, 33, 47, 48, 63, 64, 65, 255, 256, 1000, 4095, 8191, 8192, 20000, 65535]))
+        if style == 1:
+            off = int(rng.integers(1, 65536))
+        off = max(1, min(off, reach, 65535))
+        ml = int(rng.choice([4, 5, 18, 19, 20, 33, 36, 64, 65, 68, 69, 100, 273, 274, 529, 2000])) if style else int(rng.integers(4, 40))
+        ml = min(ml, target - produced - lit - 13)
+        if ml < 4:
+            break
+        tok = (min(lit, 15) << 4) | min(ml - 4, 15)
+        out.append(tok)
+        if lit >= 15:
+            _emit_len(out, lit)
+        out += plain_src[produced:produced + lit]
+        out += bytes([off & 255, off >> 8])
+        if ml - 4 >= 15:
+            _emit_len(out, ml - 4)
+        produced += lit + ml
+    last = max(target - produced, 6)                       # the block ends with >= 5 literals (12 after the last match start)
+    out.append(min(last, 15) << 4)
+    if last >= 15:
+        _emit_len(out, last)
+    out += plain_src[produced:produced + last]
+    return bytes(out), produced + last
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_handbuilt_blocks_decode_like_the_reference(ctx, ref, seed):
+    import streamly_lz4_b200 as lz
+    rng = np.random.default_rng(1000 + seed)
+    for linked in (False, True):
+        framed = []
+        prev = 0
+        for _ in range(10):
+            target = int(rng.choice([64, 300, 5000, 70000, 300000]))
+            payload, n = build_block(rng, target, prev if linked else 0)
+            framed.append(len(payload).to_bytes(4, "little") + n.to_bytes(4, "little") + payload)
+            prev = n
+        want = ref.decompress_chunks_raw(framed, linked=linked)
+        got = list(lz.decompress_chunks_raw(lz.BlockConfig(independent=not linked), framed, ctx=ctx))
+        assert [len(g) for g in got] == [len(w) for w in want]
+        for i, (g, w) in enumerate(zip(got, want)):
+            if g != w:
+                at = int(np.argmax(np.frombuffer(g, np.uint8) != np.frombuffer(w, np.uint8)))
+                raise AssertionError(f"seed {seed} linked {linked} block {i}: first difference at byte {at} of {len(w)}")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_round_trips_against_oracle(ctx, ref, seed):
+    import streamly_lz4_b200 as lz
+    from streamly_lz4_b200 import datagen
+    rng = np.random.default_rng(2000 + seed)
+    kinds = ["text", "random", "sparse01", "records", "mixed", "bits01", "biased01", "zero"]
+    for _ in range(12):
+        kind = kinds[int(rng.integers(0, len(kinds)))]
+        total = int(rng.integers(1, 400000))
+        data = datagen.make(kind, int(rng.integers(0, 1 << 30)), total)
+        cuts = np.sort(rng.integers(0, total + 1, size=int(rng.integers(0, 12))))
+        arrays = [data[a:b].tobytes() for a, b in zip(np.r_[0, cuts], np.r_[cuts, total])]   # includes empty arrays
+        accel = int(rng.choice([-3, 0, 1, 2, 7, 33, 400, 5000, 65537, 100000]))
+        linked = bool(rng.integers(0, 2))
+        cfg = lz.BlockConfig(independent=not linked)
+        got = list(lz.compress_chunks(cfg, accel, arrays, ctx=ctx))
+        want = ref.compress_chunks(arrays, accel, linked=linked)
+        assert got == want, f"{kind} total={total} accel={accel} linked={linked} cuts={list(cuts)}"
+        assert list(lz.decompress_chunks_raw(cfg, want, ctx=ctx)) == arrays
