@@ -126,3 +126,49 @@ def test_config5_mixed_block_sizes_reframe_and_sweep(ctx, ref):
         assert got == ref.compress_chunks(blocks, accel, linked=False, threads=8), f"accel {accel}"
         seen[accel] = hashlib.sha256(b"".join(got)).digest()
     assert seen[-1] == seen[0] == seen[1] and seen[65537] == seen[65538]
+
+
+def test_linked_stream_across_2gib_renorm(ctx, ref):
+    """Row a6 (LZ4_renormDictT, cbits/lz4.c:1545-1562): one linked stream whose currentOffset passes 2 GiB.
+    1.95 GiB of incompressible data at acceleration 65537 (cheap), then 320 MiB of mixed data at acceleration 1
+    through the SAME stream state; every block of the second call must equal the reference's bytes."""
+    import ctypes
+    import streamly_lz4_b200 as lz
+    from streamly_lz4_b200 import datagen
+    bs = 4 << 20
+    n1, n2 = 499, 80                                      # 1.949 GiB, then 320 MiB: the offset passes 2^31 inside call 2
+    filler = datagen.make("random", 21, bs)
+    tail = datagen.make("mixed", 22, n2 * bs)
+    # reference: one LZ4_stream_t, separately allocated arrays
+    cs = ref.ccreate()
+    bound = ref.bound(bs)
+    dst = np.zeros(bound, dtype=np.uint8)
+    blocks_a = [filler.copy() for _ in range(2)]           # alternate two allocations: never adjacent, never the same array twice in a row
+    for i in range(n1):
+        a = blocks_a[i & 1]
+        assert ref.ccont(cs, a.ctypes.data, dst.ctypes.data, bs, bound, 65537) > 0
+    want = []
+    keep = []
+    for i in range(n2):
+        a = tail[i * bs:(i + 1) * bs].copy(); keep.append(a)
+        r = ref.ccont(cs, a.ctypes.data, dst.ctypes.data, bs, bound, 1)
+        assert r > 0
+        want.append(dst[:r].tobytes())
+    ref.cfree(cs)
+    # GPU: same two calls through one device-resident stream
+    stream = lz.CompressStream(ctx)
+    src1 = np.tile(filler, n1)
+    offs1 = (np.arange(n1, dtype=np.int64) * bs); lens1 = np.full(n1, bs, dtype=np.int32)
+    out1 = ctx.pinned("rn_out", int(n1 * (bound + 8)))
+    rc, _, ol1 = ctx.compress_batch(src1, offs1, lens1, 65537, 8, out1, stream_first=np.array([0, n1], np.int32), streams=[stream])
+    assert rc == 0 and (ol1 > 0).all()
+    _, off_mid = stream.peek()
+    assert off_mid == n1 * bs
+    offs2 = (np.arange(n2, dtype=np.int64) * bs); lens2 = np.full(n2, bs, dtype=np.int32)
+    rc, doff, ol2 = ctx.compress_batch(tail, offs2, lens2, 1, 8, out1, stream_first=np.array([0, n2], np.int32), streams=[stream])
+    assert rc == 0 and (ol2 > 0).all()
+    for i in range(n2):
+        assert out1[doff[i] + 8:doff[i + 1]].tobytes() == want[i], f"block {i} after {n1} filler blocks differs"
+    _, off_end = stream.peek()
+    assert off_end < (1 << 31)                             # renormalised (the reference resets to 64 KiB + later blocks)
+    stream.free()
