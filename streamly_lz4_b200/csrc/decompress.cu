@@ -564,7 +564,6 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
                 for (uint32_t i = 0; i < lit; i++) sts8(out_s + ((dl + i) & M), lds8(in_s + ((sl + i) & (kInRing - 1))));
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&q->empty[b]);  // descriptors are in registers and the input ring is no longer needed
             // phase A: matches whose source was complete before this batch
             const bool has_match = mlen != 0;
             const bool indep = has_match && (from + (int)mlen <= op0);
@@ -605,33 +604,32 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
             // within 64 bytes of the batch start, which the ring always holds (see preload()).
             uint32_t dep = __ballot_sync(kFull, has_match && !indep);
             if (dep) {
-                const uint32_t mlds = mlen | (dist << 16);
-                int l = __ffs(dep) - 1;
-                uint32_t n_da = __shfl_sync(kFull, da, l), n_mlds = __shfl_sync(kFull, mlds, l);
+                // every lane leaves {destination, length, offset, reciprocal} of its match in the (already consumed)
+                // descriptor slot, so the loop below reads one broadcast 128-bit word per match instead of shuffling
+                const uint32_t par_s = smem_u32(&q->desc[b][0]);
+                {   // overlapping match (offset < length <= 64): byte i comes from source byte i mod offset; i mod offset
+                    // through a 16-bit fixed-point reciprocal, exact for i < 64 (inv = 65536/offset plus at most 3);
+                    // inv = 0 makes it the identity for ordinary matches
+                    const uint32_t inv = (dist < mlen) ? (uint32_t)(65536.0f * __frcp_rn((float)dist)) + 2u : 0u;
+                    sts128(par_s + 16u * lane, da, mlen, dist, inv);
+                }
+                __syncwarp();
+                const uint32_t i1 = lane + 32;
+                uint4 nx = lds128(par_s + 16u * (uint32_t)(__ffs(dep) - 1));
                 for (;;) {
                     dep &= dep - 1;
-                    const uint32_t cda = n_da, ml = n_mlds & 0xFFFFu, ds = n_mlds >> 16;
-                    if (dep) {      // the next match's parameters travel while this one is copied
-                        l = __ffs(dep) - 1;
-                        n_da = __shfl_sync(kFull, da, l); n_mlds = __shfl_sync(kFull, mlds, l);
-                    }
-                    const uint32_t csa = cda - ds;
-                    if (ds >= ml) {
-                        if (lane < ml) sts8(out_s + ((cda + lane) & M), lds8(out_s + ((csa + lane) & M)));
-                        if (lane + 32 < ml) sts8(out_s + ((cda + lane + 32) & M), lds8(out_s + ((csa + lane + 32) & M)));
-                    } else {
-                        // overlapping match (ds < ml <= 64): byte i comes from source byte i mod ds; i mod ds through a
-                        // 16-bit fixed-point reciprocal, exact for i < 64 (inv is 65536/ds plus at most 3)
-                        const uint32_t inv = (uint32_t)(65536.0f * __frcp_rn((float)ds)) + 2u;
-                        const uint32_t i1 = lane + 32;
-                        const uint32_t k0 = lane - ((lane * inv) >> 16) * ds, k1 = i1 - ((i1 * inv) >> 16) * ds;
-                        if (lane < ml) sts8(out_s + ((cda + lane) & M), lds8(out_s + ((csa + k0) & M)));
-                        if (i1 < ml) sts8(out_s + ((cda + i1) & M), lds8(out_s + ((csa + k1) & M)));
-                    }
+                    const uint4 cu = nx;
+                    if (dep) nx = lds128(par_s + 16u * (uint32_t)(__ffs(dep) - 1));      // next match's parameters, early
+                    const uint32_t csa = cu.x - cu.z;
+                    const uint32_t k0 = lane - ((lane * cu.w) >> 16) * cu.z, k1 = i1 - ((i1 * cu.w) >> 16) * cu.z;
+                    if (lane < cu.y) sts8(out_s + ((cu.x + lane) & M), lds8(out_s + ((csa + k0) & M)));
+                    if (i1 < cu.y) sts8(out_s + ((cu.x + i1) & M), lds8(out_s + ((csa + k1) & M)));
                     __syncwarp();
                     if (!dep) break;
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q->empty[b]);  // literals copied, descriptor slots no longer in use
             C.op = op1;
         } else {
             __syncwarp();
