@@ -159,6 +159,11 @@ __device__ __forceinline__ uint32_t warp_common_suffix(const uint8_t* a, const u
 //   data readable for positions [lo_pos, ready_end), hashes valid for [lo_pos, ready_end - 4).
 // All accesses use explicit 32-bit shared-space addresses (ld.shared / st.shared).
 constexpr int kWinLines = 4, kWinWords = kWinLines * 32, kWinBytes = kWinLines * 128;
+// WIDE mode (at most one stream per SM): the data ring is 128 KiB and indexed by stream position, so it holds the
+// previous array too -- every candidate within reach (65535 back, dictionary included), every catch-up and every
+// count is then served from shared memory and a block costs its instruction chain, not L2 round trips.
+constexpr int kWideLines = 1024, kWideBytes = kWideLines * 128;
+constexpr int kHashPos = 512;                    // hash ring: u16 hashes of the 512 most recent ring positions
 
 __device__ __forceinline__ void cp_async_4(uint32_t smem_addr, const void* g)
 { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory"); }
@@ -179,6 +184,9 @@ struct BlockIn {
     uint32_t start;             // currentOffset before this block
     int accel;
     int block;                  // block index (for the emitter)
+    // wide mode, carried from block to block of a stream: ring position one past the previous array, lowest ring
+    // position of contiguously loaded data, and whether both mean anything
+    uint32_t w_end, w_lo; bool w_ok;
 };
 
 // Producer side of the queue (finder warp).  The buffer being filled is always already acquired.
@@ -219,9 +227,11 @@ __device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t mask, uint32_t b
 
 // Match finder for one block: pushes sequence descriptors, ends with the final-literals descriptor.
 // data_s (512-byte aligned) / hash_s (1024-byte aligned): shared addresses of this finder's rings.
-__device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t data_s, const uint32_t hash_s, Producer& out,
+template <bool kWide>
+__device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, const uint32_t hash_s, Producer& out,
                            const uint32_t off0, const uint32_t step0, const uint32_t off1, const uint32_t step1)
 {
+    constexpr uint32_t kRingBytes = kWide ? kWideBytes : kWinBytes;
     const uint32_t lane = lane_id();
     const uint8_t* const src = in.src;
     const int n = in.n;
@@ -232,34 +242,52 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
     const int mlimit = n - kLastLiterals;      // matchlimit
     const uint32_t table_s = smem_u32(table);
     int anchor = 0;
+    if (kWide && n < kMinLength) in.w_ok = false;       // nothing of a tiny array reaches the ring
 
     if (n >= kMinLength) {
         // ---- window state (see the invariant above)
         const uintptr_t base = reinterpret_cast<uintptr_t>(src), end = base + (uintptr_t)n;
-        const uint32_t g32 = (uint32_t)base;
+        // Ring position of block position p is g32 + p (as u32).  Dense mode: g32 = the block's global address, the
+        // ring is a 512-byte cache of the lines around ip.  Wide mode: g32 continues the previous array's positions
+        // when the word alignment of both agrees, so positions below 0 are the dictionary, still resident.
+        uint32_t g32 = (uint32_t)base;
+        int lo_pos = 0;                        // lowest block position whose bytes are in the ring (wide: may be negative)
+        if (kWide) {
+            if (in.w_ok && in.dict_len && ((in.w_end - g32) & 3u) == 0 && (base & 3) == 0) {
+                g32 = in.w_end;
+                const uint32_t have = in.w_end - in.w_lo;           // contiguously loaded bytes before this block
+                lo_pos = -(int)min(min(have, in.dict_len), (uint32_t)(kWideBytes - 65536 - 1024));
+            }
+            in.w_ok = false;
+        }
         const uint32_t glane = g32 + 4 * lane;
         uintptr_t cur_line = ~uintptr_t(0) - 8;
-        int lo_pos = 0, ready_end = 0, trigger = -1;
+        int ready_end = 0, trigger = -1;
         uint32_t pf_next = 0;                  // next input byte not yet requested into L2
 
-        auto ring32 = [&](uint32_t a) {        // 4 bytes of the data ring at truncated global address a
-            return __funnelshift_r(lds32(and_or(a, kWinBytes - 4, data_s)), lds32(and_or(a + 4, kWinBytes - 4, data_s)), a << 3);
+        auto raddr = [&](uint32_t a, uint32_t mask) -> uint32_t {     // shared address of ring position a (mask selects the granule)
+            if (kWide) return data_s + (a & mask);
+            return and_or(a, mask, data_s);
         };
-        auto hash_at = [&](uint32_t a) { return lds16(and_or(a << 1, 2 * kWinBytes - 2, hash_s)); };
+        auto ring32 = [&](uint32_t a) {        // 4 bytes of the data ring at ring position a
+            return __funnelshift_r(lds32(raddr(a, kRingBytes - 4)), lds32(raddr(a + 4, kRingBytes - 4)), a << 3);
+        };
+        auto ring8 = [&](uint32_t a) { return lds8(raddr(a, kRingBytes - 1)); };
+        auto hash_at = [&](uint32_t a) { return lds16(and_or(a << 1, 2 * kHashPos - 2, hash_s)); };
         auto issue = [&](uintptr_t line) {     // one 4-byte cp.async per lane; lines outside the block are not touched
             const uintptr_t wa = (line << 7) + 4 * lane;       // this lane's aligned word: copied only if it holds a byte of the block
             if (wa < end && wa + 4 > base)
-                cp_async_4(data_s + (uint32_t)(((line & (kWinLines - 1)) * 32 + lane) * 4), reinterpret_cast<const void*>(wa));
+                cp_async_4(raddr(g32 + (uint32_t)(wa - base), kRingBytes - 4), reinterpret_cast<const void*>(wa));
             cp_async_commit();
         };
         auto hash_round = [&](int p0) {        // hashes of the 128 positions from p0 on ((g32 + p0) % 4 == 0)
             const uint32_t a = glane + (uint32_t)p0;
-            const uint32_t w0 = lds32(and_or(a, kWinBytes - 4, data_s)), w1 = lds32(and_or(a + 4, kWinBytes - 4, data_s));
+            const uint32_t w0 = lds32(raddr(a, kRingBytes - 4)), w1 = lds32(raddr(a + 4, kRingBytes - 4));
             const uint32_t h0 = hash5(w0, w1 & 0xFFu);
             const uint32_t h1 = hash5(__funnelshift_r(w0, w1, 8), (w1 >> 8) & 0xFFu);
             const uint32_t h2 = hash5(__funnelshift_r(w0, w1, 16), (w1 >> 16) & 0xFFu);
             const uint32_t h3 = hash5(__funnelshift_r(w0, w1, 24), w1 >> 24);
-            sts64(and_or(a << 1, 2 * kWinBytes - 8, hash_s), h0 | (h1 << 16), h2 | (h3 << 16));
+            sts64(and_or(a << 1, 2 * kHashPos - 8, hash_s), h0 | (h1 << 16), h2 | (h3 << 16));
         };
         auto l2_prefetch = [&](int ip) {       // keep the next kPrefetchAhead bytes of input on their way into L2
             if (pf_next < (uint32_t)ip) pf_next = (uint32_t)ip & ~(kPrefetchChunk - 1);
@@ -276,6 +304,33 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
             __syncwarp();
             cp_async_wait<0>();
             __syncwarp();
+            if (kWide) {
+                // the ring keeps everything behind ip: advance over up to 96 lines without leaving a hole
+                const bool near = trigger >= 0 && L > cur_line && L - cur_line <= 96;
+                int new_ready;
+                if (near) {
+                    for (uintptr_t l = cur_line + 3; l <= L + 1; l++) issue(l);
+                    if (L > cur_line + 1) { cp_async_wait<0>(); __syncwarp(); }
+                    new_ready = (int)(((L + 2) << 7) - base);
+                } else {                       // first window of the block, or a long skip (leaves a hole behind it)
+                    issue(L - 1); issue(L); issue(L + 1);
+                    cp_async_wait<0>();
+                    __syncwarp();
+                    const long long lo = (long long)((L - 1) << 7) - (long long)base;
+                    if (lo > 0) lo_pos = (int)lo;           // else: the window reaches the block start, what precedes it stays valid
+                    new_ready = (int)lo + 384;
+                    hash_round((int)lo); hash_round((int)lo + 128); hash_round((int)lo + 256);
+                }
+                if (near) for (int r = max(ready_end, new_ready - 384); r < new_ready; r += 128) hash_round(r - 4);
+                ready_end = new_ready;
+                lo_pos = max(lo_pos, new_ready + 128 - kWideBytes);
+                issue(L + 2);
+                __syncwarp();
+                cur_line = L;
+                trigger = (int)(((L + 1) << 7) - base);
+                if ((uint32_t)ip + kPrefetchAhead > pf_next) l2_prefetch(ip);
+                return;
+            }
             if (L == cur_line + 1) {           // steady state: line L+1 has just landed
                 hash_round(ready_end - 4);
                 ready_end += 128;
@@ -302,9 +357,101 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
         // verify+count).  kRetest: the post-match probe, which first inserts p-2 and has no literals.
         // On a hit fills mip / mlen / dist and returns true.
         int mip = 0; uint32_t mlen = 0, dist = 0;
+
+        // ---- wide mode: extensions served from the ring.  Block positions; c < p; c may be negative (dictionary).
+        // common prefix of p.. and c.., at most cap, as far as the ring reaches; `more`: the ring ended first
+        auto ring_prefix = [&](int p, int c, uint32_t cap, bool& more) -> uint32_t {
+            const uint32_t lim = min(cap, (uint32_t)(ready_end - p));
+            const uint32_t pa = g32 + (uint32_t)p, ca = g32 + (uint32_t)c;
+            uint32_t k0 = 0;
+            for (;;) {
+                const uint32_t at = k0 + lane * 4;
+                uint32_t nb = 0;
+                bool stop = true;
+                if (at + 4 <= lim) {
+                    const uint32_t x = ring32(pa + at) ^ ring32(ca + at);
+                    nb = x ? ((uint32_t)(__ffs(x) - 1) >> 3) : 4u;
+                    stop = (nb < 4);
+                } else if (at < lim) {
+                    const uint32_t room = lim - at;
+                    while (nb < room && ring8(pa + at + nb) == ring8(ca + at + nb)) nb++;
+                }
+                const uint32_t sb = __ballot_sync(kFull, stop);
+                if (sb) {
+                    uint32_t res = __shfl_sync(kFull, at + nb, __ffs(sb) - 1);
+                    res = res < lim ? res : lim;
+                    more = (res == lim) && (lim < cap);
+                    return res;
+                }
+                k0 += 128;
+            }
+        };
+        // full forward count: ring first, then global memory (two segments when the candidate is still in the dictionary)
+        auto count_wide = [&](int p, int c, uint32_t cap) -> uint32_t {
+            bool more = false;
+            uint32_t L = ring_prefix(p, c, cap, more);
+            if (more) {
+                int cc = c + (int)L;
+                const uint8_t* a = src + p + L;
+                uint32_t rest = cap - L;
+                if (cc < 0) {                                                                        // :1080-1089
+                    const uint32_t seg = min(rest, (uint32_t)(-cc));
+                    const uint32_t x = warp_common_prefix(a, in.dict_end + cc, seg);
+                    L += x;
+                    if (x < seg || rest == seg) return L;
+                    a += x; rest -= x; cc = 0;
+                }
+                L += warp_common_prefix(a, src + cc, rest);
+            }
+            return L;
+        };
+        // number of equal bytes walking backwards from p-1 / c-1, at most cap; needs c - cap >= lo_pos
+        auto ring_suffix = [&](int p, int c, uint32_t cap) -> uint32_t {
+            const uint32_t pa = g32 + (uint32_t)p, ca = g32 + (uint32_t)c;
+            uint32_t k0 = 0;
+            for (;;) {
+                const uint32_t at = k0 + lane * 4;
+                uint32_t nb = 0;
+                bool stop = true;
+                if (at + 4 <= cap) {
+                    const uint32_t x = ring32(pa - at - 4) ^ ring32(ca - at - 4);
+                    nb = x ? ((uint32_t)__clz(x) >> 3) : 4u;
+                    stop = (nb < 4);
+                } else if (at < cap) {
+                    const uint32_t room = cap - at;
+                    while (nb < room && ring8(pa - at - nb - 1) == ring8(ca - at - nb - 1)) nb++;
+                }
+                const uint32_t sb = __ballot_sync(kFull, stop);
+                if (sb) {
+                    const uint32_t res = __shfl_sync(kFull, at + nb, __ffs(sb) - 1);
+                    return res < cap ? res : cap;
+                }
+                k0 += 128;
+            }
+        };
         // verify candidate index m for position p and count the match (table already updated)
         auto verify_count = [&](int p, uint32_t m, bool retest) -> bool {
             const uint32_t cur = S + (uint32_t)p;
+            if (kWide) {
+                const int cpos = (int)(m - S);                      // negative: in the dictionary, still a ring position
+                if (cpos >= lo_pos) {
+                    uint32_t L = count_wide(p, cpos, (uint32_t)(mlimit - p));
+                    if (L < 4) return false;                                                         // :1009 / :1189
+                    uint32_t back = 0;
+                    if (!retest) {                                                                   // :1019
+                        const uint32_t room_c = (m >= S) ? (uint32_t)cpos : in.dict_len - (S - m);
+                        const uint32_t real = min((uint32_t)(p - anchor), room_c);
+                        const uint32_t in_ring = min(real, (uint32_t)(cpos - lo_pos));      // part of the walk the ring can serve
+                        if (in_ring && ring8(g32 + (uint32_t)p - 1) == ring8(g32 + (uint32_t)cpos - 1)) back = ring_suffix(p, cpos, in_ring);
+                        if (back == in_ring && back < real) {       // the ring ended before the walk did: finish it in global memory
+                            const uint8_t* cand_g = (m >= S) ? (src + cpos) : (in.dict_end - (S - m));
+                            back += warp_common_suffix(src + p - back, cand_g - back, real - back);
+                        }
+                    }
+                    mip = p - (int)back; mlen = L + back; dist = cur - m;
+                    return true;
+                }
+            }
             const uint32_t mine = ring32(glane + (uint32_t)p);      // lane's 4 bytes of p..
             uint32_t cap = (uint32_t)(mlimit - p);
             uint32_t L;
@@ -359,24 +506,28 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
             if (p >= trigger) move_window(p);
             const uint32_t ap = g32 + (uint32_t)p;
             const uint32_t capb = min((uint32_t)(mlimit - p), 32u);
-            const uint32_t mine = lds8(and_or(ap + lane, kWinBytes - 1, data_s));     // issued early: overlaps the table chain
+            const uint32_t mine = ring8(ap + lane);             // issued early: overlaps the table chain
             const uint32_t h = hash_at(ap);
             const uint32_t cur = S + (uint32_t)p;
             sts32(table_s + hash_at(ap - 2) * 4, cur - 2);                                           // :1146
             const uint32_t m = lds32(table_s + h * 4);
             sts32(table_s + h * 4, cur);                                                             // :1185
             if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) return false;             // :1187-1188
-            if (m < S) return verify_count(p, m, true);                                              // candidate in the dictionary
             const int cpos = (int)(m - S);
+            if (m < S && !(kWide && cpos >= lo_pos)) return verify_count(p, m, true);                // candidate in the dictionary, not in the ring
             uint32_t theirs = 0x100u;                           // lanes past the cap differ by construction
             if (lane < capb)
-                theirs = (cpos >= lo_pos) ? lds8(and_or(g32 + (uint32_t)cpos + lane, kWinBytes - 1, data_s)) : (uint32_t)__ldg(src + cpos + lane);
+                theirs = (cpos >= lo_pos) ? ring8(g32 + (uint32_t)cpos + lane) : (uint32_t)__ldg(src + cpos + lane);
             const uint32_t ne = __ballot_sync(kFull, mine != theirs);
             uint32_t L;
             if (ne) L = (uint32_t)__ffs(ne) - 1u;
             else {                                              // 32 equal bytes and room for more
                 const uint32_t cap = (uint32_t)(mlimit - p);
-                L = 32u + (cap > 32u ? warp_common_prefix(src + p + 32, src + cpos + 32, cap - 32u) : 0u);
+                L = 32u;
+                if (cap > 32u) {
+                    if (kWide && cpos >= lo_pos) L += count_wide(p + 32, cpos + 32, cap - 32u);
+                    else L += warp_common_prefix(src + p + 32, src + cpos + 32, cap - 32u);
+                }
             }
             if (L < 4) return false;                                                                 // :1189
             mip = p; mlen = L; dist = cur - m;
@@ -444,8 +595,12 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
                     if (valid) {
                         m = lower ? fwd : lds32(table_s + h * 4);
                         if (!(dict_small && m < low_index) && (m + kMaxDistance >= cur)) {           // :1001-1006
-                            const uint8_t* c = (m < S) ? (in.dict_end - (S - m)) : (src + (m - S));  // :985-993
-                            ok = (ldg_u32_unaligned(c) == seq);                                      // :1009
+                            if (kWide && (int)(m - S) >= lo_pos && (int)(m - S) + 4 <= ready_end) {      // (a run may have outrun the loaded lines)
+                                ok = (ring32(g32 + (m - S)) == seq);
+                            } else {
+                                const uint8_t* c = (m < S) ? (in.dict_end - (S - m)) : (src + (m - S));  // :985-993
+                                ok = (ldg_u32_unaligned(c) == seq);                                  // :1009
+                            }
                         }
                     }
                     const uint32_t okb = __ballot_sync(kFull, ok);
@@ -475,6 +630,11 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
                 // The backward and the forward extension are independent: the byte pair that decides whether there
                 // is anything to catch up is requested before the forward count, so both round trips overlap.
                 const bool in_dict = midx < S;
+                if (kWide && (int)(midx - S) >= lo_pos && mpos + 4 <= ready_end) {
+                    // 4 bytes are known equal; verify_count redoes them from the ring and handles catch-up
+                    const bool hit = verify_count(mpos, midx, false);
+                    (void)hit;                  // always true: the candidate was accepted on the same bytes
+                } else {
                 const uint8_t* cand = in_dict ? (in.dict_end - (S - midx)) : (src + (midx - S));
                 const uint32_t room_c = in_dict ? (in.dict_len - (S - midx)) : (midx - S);
                 const uint32_t maxback = min((uint32_t)(mpos - anchor), room_c);
@@ -488,6 +648,7 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
                 const uint32_t back = (b_src == b_cand) ? warp_common_suffix(src + mpos, cand, maxback) : 0u;
                 mip = mpos - (int)back;
                 mlen = L + back; dist = (S + (uint32_t)mpos) - midx;
+                }
             }
             out.push((uint32_t)anchor, (uint32_t)(mip - anchor), mlen - 4, dist, in.block);
             ip = mip + (int)mlen;
@@ -496,6 +657,10 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
             after_match = true;
         }
     tail:
+        if (kWide) {                    // this array is the next block's dictionary: bring its tail into the ring
+            if (n - 1 >= trigger) move_window(n - 1);
+            in.w_end = g32 + (uint32_t)n; in.w_lo = g32 + (uint32_t)lo_pos; in.w_ok = true;
+        }
         cp_async_wait<0>();             // nothing of this block's window may land after the next block starts
         __syncwarp();
     }
@@ -503,6 +668,7 @@ __device__ void find_block(const BlockIn& in, uint32_t* table, const uint32_t da
     out.push((uint32_t)anchor, (uint32_t)(n - anchor), 0u, 0u, in.block);
 }
 
+template <bool kWide>
 __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ring, uint16_t* hring, Queue* q)
 {
     const uint32_t lane = lane_id();
@@ -539,6 +705,7 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ri
             __syncwarp();
         }
         const uint8_t* last_src = nullptr; int last_n = -1;
+        uint32_t w_end = 0, w_lo = 0; bool w_ok = false;
         for (int b = b0; b < b1; b++) {
             const uint8_t* src = a.src + a.src_off[b];
             const int n = a.src_len[b];
@@ -551,15 +718,17 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ri
                     __syncwarp();
                 }
                 if (dict_len >= 1 && dict_len <= 3) dict_len = 0;                            // :1581-1587
-                BlockIn in{src, n, dict_end, dict_len, offset, accel, b};
+                BlockIn in{src, n, dict_end, dict_len, offset, accel, b, w_end, w_lo, w_ok};
                 if (n > 0) offset += (uint32_t)n;                                            // :918 (n == 0 never reaches it, :1263-1273)
-                find_block(in, table, data_s, hash_s, out, (uint32_t)off0, (uint32_t)step0, (uint32_t)off1, (uint32_t)step1);
+                find_block<kWide>(in, table, data_s, hash_s, out, (uint32_t)off0, (uint32_t)step0, (uint32_t)off1, (uint32_t)step1);
+                w_end = in.w_end; w_lo = in.w_lo; w_ok = in.w_ok;
                 __syncwarp();
                 dict_end = src + n; dict_len = (uint32_t)n;                                  // :1633-1634
                 last_src = src; last_n = n;
                 out.flush(b, kEndBlock);
             } else {
                 out.flush(b, kEndBlock | (1 << 28));      // unsupported size: the emitter reports 0
+                w_ok = false;
             }
         }
         if (st) {   // persist the stream (what the reference keeps in LZ4_stream_t + the live previous array)
@@ -677,7 +846,7 @@ compress_kernel(CompressArgs a)
     // layout (from a 1024-byte aligned start): hash rings | data rings | tables | queues
     uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint16_t* hrings = reinterpret_cast<uint16_t*>(smem_raw);
-    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw + kPairs * kWinBytes * sizeof(uint16_t));
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw + kPairs * kHashPos * sizeof(uint16_t));
     uint32_t* tables = rings + kPairs * kWinWords;
     Queue* queues = reinterpret_cast<Queue*>(tables + kPairs * kHashEntries);
     const uint32_t warp = threadIdx.x >> 5;
@@ -688,9 +857,37 @@ compress_kernel(CompressArgs a)
         mbar_init(&q->empty[0], 1); mbar_init(&q->empty[1], 1);
     }
     __syncthreads();
-    if (warp < kPairs) finder_main(a, tables + pair * kHashEntries, rings + pair * kWinWords, hrings + pair * kWinBytes, &queues[pair]);
+    if (warp < kPairs) finder_main<false>(a, tables + pair * kHashEntries, rings + pair * kWinWords, hrings + pair * kHashPos, &queues[pair]);
     else emitter_main(a, &queues[pair]);
     // last CTA out resets the work counter so the scratch stays zeroed for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t done = atomicAdd(&a.scratch->work_counter[1], 1u);
+        if (done == gridDim.x - 1) { a.scratch->work_counter[0] = 0; a.scratch->work_counter[1] = 0; __threadfence(); }
+    }
+}
+
+// Wide mode: one finder/emitter pair per CTA, one CTA per SM (144 KiB: hash ring | 128 KiB data ring | table | queue).
+// Used when a launch has no more streams than the device has SMs (few linked streams, few large blocks, the tail
+// chunk of a host batch): per-stream latency is all that matters then.
+constexpr size_t kWideSmem = 1024 /* alignment slack */ + kHashPos * sizeof(uint16_t) + kWideBytes + kHashEntries * sizeof(uint32_t) + sizeof(Queue);
+
+__global__ void __launch_bounds__(64, 1)
+compress_kernel_wide(CompressArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_dyn[];
+    uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint16_t* hring = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + kHashPos * sizeof(uint16_t));
+    uint32_t* table = ring + kWideBytes / 4;
+    Queue* q = reinterpret_cast<Queue*>(table + kHashEntries);
+    if (threadIdx.x == 0) {
+        mbar_init(&q->full[0], 1); mbar_init(&q->full[1], 1);
+        mbar_init(&q->empty[0], 1); mbar_init(&q->empty[1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) finder_main<true>(a, table, ring, hring, q);
+    else emitter_main(a, q);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t done = atomicAdd(&a.scratch->work_counter[1], 1u);
@@ -704,13 +901,15 @@ cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
 {
     static int sm_counts[64] = {0};     // per device: SM count, 0 = kernel not configured there yet
     const size_t smem = kPairs * kHashEntries * sizeof(uint32_t) + kPairs * sizeof(Queue) + kPairs * kWinWords * sizeof(uint32_t)
-                        + kPairs * kWinBytes * sizeof(uint16_t) + 1024 /* alignment slack */;
+                        + kPairs * kHashPos * sizeof(uint16_t) + 1024 /* alignment slack */;
     int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!sm_counts[dev]) {
         int n = 0;
         e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(compress_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
         if (e != cudaSuccess) return e;
         sm_counts[dev] = n;
         if (getenv("B200LZ4_DEBUG")) {
@@ -721,6 +920,11 @@ cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
     }
     const int sm_count = sm_counts[dev];
     if (a.n_streams <= 0) return cudaSuccess;
+    static const bool no_wide = getenv("B200LZ4_NO_WIDE") != nullptr;     // A/B switch for measurements
+    if (a.n_streams <= sm_count && !no_wide) {   // few streams: one per SM with everything in shared memory
+        compress_kernel_wide<<<a.n_streams, 64, kWideSmem, stream>>>(a);
+        return cudaGetLastError();
+    }
     const int ctas_per_sm = 3;                   // 3 x (64 KiB of tables + queues) per SM
     const int max_ctas = sm_count * ctas_per_sm;
     const int want = (a.n_streams + kPairs - 1) / kPairs;
