@@ -682,11 +682,13 @@ decompress_kernel(DecompressArgs a)
 
 cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream)
 {
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
+    static int sm_counts[64] = {0};     // per device
+    int dev = 0; cudaError_t e0 = cudaGetDevice(&dev); if (e0 != cudaSuccess) return e0;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!sm_counts[dev]) {
+        e0 = cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev); if (e0 != cudaSuccess) return e0;
     }
+    const int sm_count = sm_counts[dev];
     if (a.n_streams <= 0) return cudaSuccess;
     const int max_ctas = sm_count * 16;
     const int grid = a.n_streams < max_ctas ? a.n_streams : max_ctas;
