@@ -126,6 +126,12 @@ __device__ __forceinline__ uint32_t warp_common_prefix(const uint8_t* a, const u
 __device__ __forceinline__ uint32_t warp_common_suffix(const uint8_t* a, const uint8_t* b, uint32_t cap)
 {
     const uint32_t lane = lane_id();
+    if (cap <= 32) {                    // the usual case (a few literals at most): one byte per lane, one ballot
+        uint32_t x = 0, y = 1;          // lanes at or past the cap differ by construction
+        if (lane < cap) { x = __ldg(a - 1 - lane); y = __ldg(b - 1 - lane); }
+        const uint32_t ne = __ballot_sync(kFull, x != y);
+        return ne ? (uint32_t)__ffs(ne) - 1u : 32u;     // ne == 0 only when cap == 32 and all 32 bytes agree
+    }
     uint32_t base = 0;
     for (;;) {
         const uint32_t at = base + lane * 4;        // this lane covers bytes [-(at+4), -at)
@@ -408,6 +414,12 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
         // number of equal bytes walking backwards from p-1 / c-1, at most cap; needs c - cap >= lo_pos
         auto ring_suffix = [&](int p, int c, uint32_t cap) -> uint32_t {
             const uint32_t pa = g32 + (uint32_t)p, ca = g32 + (uint32_t)c;
+            if (cap <= 32) {            // the usual case: one byte per lane, one ballot
+                uint32_t x = 0, y = 1;
+                if (lane < cap) { x = ring8(pa - 1 - lane); y = ring8(ca - 1 - lane); }
+                const uint32_t ne = __ballot_sync(kFull, x != y);
+                return ne ? (uint32_t)__ffs(ne) - 1u : 32u;
+            }
             uint32_t k0 = 0;
             for (;;) {
                 const uint32_t at = k0 + lane * 4;
