@@ -278,17 +278,8 @@ def run_gpu(args):
     assert rc == 0 and int(doff[-1]) == comp_total
     clocks = sampler.stop() if rank == 0 else None
 
-    # parity spot-check inside the bench: GPU bytes of a few blocks == oracle bytes (checker only, not timed)
+    # (the cpu_baseline leg below also spot-checks a few of these GPU blocks against the oracle's bytes)
     parity = None
-    if rank == 0 and not args.no_check:
-        from oracle.oracle import Oracle
-        ora = Oracle("auto")
-        idx = sorted(set([0, n // 2, n - 1]))
-        ok = True
-        for i in idx:
-            a = host[offs[i]:offs[i] + lens[i]].tobytes()
-            ok &= pin_dst[doff[i]:doff[i + 1]].tobytes() == ora.compress_chunks([a], ACCEL, linked=False)[0]
-        parity = {"blocks_checked": idx, "byte_identical_to_oracle": bool(ok), "oracle": ora.kind}
 
     # ---- decompress of the same stream (extra, not the headline): d+640000 on the compressed output
     extra = {}
@@ -379,6 +370,16 @@ def run_gpu(args):
             dv["roofline"]["traffic"] = traffic.get("decompress_kernel_dram_bytes")
         cpu = None
         if not args.no_cpu:
+            # ---- cpu_baseline leg: the only place of this arm that touches oracle/ (timing + a parity spot check)
+            if not args.no_check:
+                from oracle.oracle import Oracle
+                ora = Oracle("auto")
+                idx = sorted(set([0, n // 2, n - 1]))
+                ok = True
+                for i in idx:
+                    a = host[offs[i]:offs[i] + lens[i]].tobytes()
+                    ok &= pin_dst[doff[i]:doff[i + 1]].tobytes() == ora.compress_chunks([a], ACCEL, linked=False)[0]
+                parity = {"blocks_checked": idx, "byte_identical_to_oracle": bool(ok), "oracle": ora.kind}
             cores = os.cpu_count() or 1
             threads = min(cores, 256)
             r_all = cpu_reference(host, offs, lens, threads, 3)

@@ -777,7 +777,7 @@ __device__ void emitter_main(const CompressArgs& a, Queue* q)
     bool failed = false;
     for (;;) {
         const uint32_t b = batch & 1, t = batch >> 1;
-        while (!mbar_test(&q->full[b], t & 1)) __nanosleep(1000);      // idle emitters must not steal issue slots from finders
+        while (!mbar_test(&q->full[b], t & 1)) __nanosleep(2500);      // idle emitters must not steal issue slots from finders (a queue buffer takes the finder >= 6 us to fill)
         const int cnt_flags = q->count[b];
         const int blk = q->block[b];
         const int cnt = cnt_flags & 0xFFFF;
