@@ -93,3 +93,32 @@ def test_random_round_trips_against_oracle(ctx, ref, seed):
         want = ref.compress_chunks(arrays, accel, linked=linked)
         assert got == want, f"{kind} total={total} accel={accel} linked={linked} cuts={list(cuts)}"
         assert list(lz.decompress_chunks_raw(cfg, want, ctx=ctx)) == arrays
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_linked_streams_split_over_random_batches(ctx, ref, seed):
+    """One linked stream pushed through the library in random batch sizes (device-resident stream state carried from
+    call to call, including tiny and empty arrays) must equal the reference's single pass, both ways; the same for
+    hand-built blocks whose matches reach into the previous output."""
+    import streamly_lz4_b200 as lz
+    from streamly_lz4_b200 import datagen
+    rng = np.random.default_rng(3000 + seed)
+    kind = ["text", "mixed", "records", "biased01"][seed % 4]
+    total = int(rng.integers(200000, 900000))
+    data = datagen.make(kind, 40 + seed, total)
+    cuts = np.sort(rng.integers(0, total + 1, size=int(rng.integers(5, 40))))
+    arrays = [data[a:b].tobytes() for a, b in zip(np.r_[0, cuts], np.r_[cuts, total])]
+    accel = int(rng.choice([1, 1, 3, 50]))
+    want = ref.compress_chunks(arrays, accel, linked=True)
+    for batch_arrays in (1, int(rng.integers(2, 6)), int(rng.integers(6, 20))):
+        got = list(lz.compress_chunks(lz.BlockConfig(), accel, arrays, ctx=ctx, batch_arrays=batch_arrays))
+        assert got == want, f"{kind} accel={accel} batch_arrays={batch_arrays}"
+        assert list(lz.decompress_chunks_raw(lz.BlockConfig(), want, ctx=ctx, batch_arrays=batch_arrays)) == arrays
+    framed, prev = [], 0
+    for _ in range(12):
+        payload, n = build_block(rng, int(rng.choice([40, 64, 300, 5000, 70000])), prev)
+        framed.append(len(payload).to_bytes(4, "little") + n.to_bytes(4, "little") + payload)
+        prev = n
+    plain = ref.decompress_chunks_raw(framed, linked=True)
+    for batch_arrays in (1, 2, 5):
+        assert list(lz.decompress_chunks_raw(lz.BlockConfig(), framed, ctx=ctx, batch_arrays=batch_arrays)) == plain
