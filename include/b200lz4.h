@@ -200,6 +200,17 @@ int b200lz4_reframe(const void* buf, int64_t len, int header_mode, int has_end_m
                     int64_t* block_off, int32_t* block_len, int64_t max_blocks,
                     int64_t* n_found, int64_t* consumed, int* ended);
 
+/*
+ * The same header walk for a stream that is already in HBM (section 8f rank 4: data that never touches the host):
+ * one thread follows the compLen chain of d_buf[0..len) and fills d_block_off / d_block_len (device arrays of
+ * max_blocks entries, usable directly as src_off / src_len of b200lz4_decompress_dev) and
+ * d_result[0..2] = {n_found, consumed, ended}; d_result[3] = 1 if a header carried compLen <= 0 (B200LZ4_E_FRAME).
+ * Only enqueues work on cuda_stream.
+ */
+int b200lz4_reframe_dev(const void* d_buf, int64_t len, int header_mode, int has_end_mark,
+                        int64_t* d_block_off, int32_t* d_block_len, int64_t max_blocks,
+                        int64_t* d_result, void* cuda_stream);
+
 /* ------------------------------------------------------ legacy aliases -- */
 /* Same names, signatures and return conventions as the 7 symbols the unmodified reference
  * imports (src/Streamly/Internal/LZ4.hs:105-140; cbits/lz4.h:170,182,273-274,336,358-359,409).

@@ -744,6 +744,18 @@ int b200lz4_reframe(const void* buf, int64_t len, int header_mode, int has_end_m
     return 0;
 }
 
+int b200lz4_reframe_dev(const void* d_buf, int64_t len, int header_mode, int has_end_mark,
+                        int64_t* d_block_off, int32_t* d_block_len, int64_t max_blocks,
+                        int64_t* d_result, void* cuda_stream)
+{
+    if (!d_result || len < 0 || (len > 0 && !d_buf) || max_blocks < 0 || (max_blocks > 0 && (!d_block_off || !d_block_len)))
+        return fail(B200LZ4_E_ARG, "NULL argument");
+    if (header_mode != 4 && header_mode != 8) return fail(B200LZ4_E_ARG, "header_mode must be 4 or 8");
+    CU(launch_reframe(static_cast<const uint8_t*>(d_buf), len, header_mode, has_end_mark, d_block_off, d_block_len, max_blocks,
+                      d_result, static_cast<cudaStream_t>(cuda_stream)));
+    return 0;
+}
+
 // ------------------------------------------------------------ legacy aliases
 
 struct LZ4_stream_u { b200lz4_cstream* s; };

@@ -80,7 +80,38 @@ gather_kernel(CompactArgs a)
     }
 }
 
+// resizeChunksD's `process` (src/Streamly/Internal/LZ4.hs:459-484) over a stream resident in HBM: a dependent chain of
+// one 4-byte load per block, so one thread walks it (O(#blocks); 13 422 blocks of config 3 take a few milliseconds).
+__global__ void reframe_kernel(const uint8_t* __restrict__ buf, long long len, int header, int has_end_mark,
+                               int64_t* __restrict__ block_off, int32_t* __restrict__ block_len, long long max_blocks,
+                               int64_t* __restrict__ result)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long at = 0, k = 0, ended = 0, bad = 0;
+    while (k < max_blocks) {
+        const long long rest = len - at;
+        if (rest < 4) break;                                            // LZ4.hs:461-462
+        const uint8_t* p = buf + at;
+        const int comp = (int)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+        if (has_end_mark && comp == 0) { at += 4; ended = 1; break; }   // LZ4.hs:464-466
+        if (rest <= header) break;                                      // LZ4.hs:468-469
+        if (comp <= 0) { bad = 1; break; }
+        const long long required = (long long)comp + header;            // LZ4.hs:474
+        if (rest < required) break;                                     // LZ4.hs:477-478
+        block_off[k] = at; block_len[k] = (int32_t)required;
+        k++; at += required;
+    }
+    result[0] = k; result[1] = at; result[2] = ended; result[3] = bad;
+}
+
 }  // namespace
+
+cudaError_t launch_reframe(const uint8_t* buf, int64_t len, int header, int has_end_mark,
+                           int64_t* block_off, int32_t* block_len, int64_t max_blocks, int64_t* result, cudaStream_t stream)
+{
+    reframe_kernel<<<1, 32, 0, stream>>>(buf, (long long)len, header, has_end_mark, block_off, block_len, (long long)max_blocks, result);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_compact(const CompactArgs& a, cudaStream_t stream)
 {

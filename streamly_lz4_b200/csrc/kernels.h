@@ -35,6 +35,8 @@ struct CompactArgs {
 cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream);
 cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream);
 cudaError_t launch_compact(const CompactArgs& a, cudaStream_t stream);
+cudaError_t launch_reframe(const uint8_t* buf, int64_t len, int header, int has_end_mark,
+                           int64_t* block_off, int32_t* block_len, int64_t max_blocks, int64_t* result, cudaStream_t stream);
 int kernel_launches_per_compress();
 int kernel_launches_per_decompress();
 int kernel_launches_per_compact();

@@ -172,3 +172,44 @@ def test_linked_stream_across_2gib_renorm(ctx, ref):
     _, off_end = stream.peek()
     assert off_end < (1 << 31)                             # renormalised (the reference resets to 64 KiB + later blocks)
     stream.free()
+
+
+def test_device_reframe_feeds_device_decode(ctx, ref):
+    """b200lz4_reframe_dev: the header walk on a stream that is already in HBM must report the same blocks as the host
+    walk, and its output arrays feed b200lz4_decompress_dev directly (no host round trip)."""
+    import ctypes
+    import torch
+    import streamly_lz4_b200 as lz
+    from streamly_lz4_b200 import _lib, datagen
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    sizes = np.exp(rng.uniform(np.log(4096), np.log(1 << 20), 200)).astype(np.int64)
+    total = int(sizes.sum())
+    data = datagen.make("mixed", 9, total)
+    offs = np.zeros(len(sizes), dtype=np.int64); offs[1:] = np.cumsum(sizes[:-1])
+    arrays = [data[o:o + s].tobytes() for o, s in zip(offs, sizes)]
+    framed = ref.compress_chunks(arrays, 1, linked=False, threads=8)
+    for end_mark in (0, 1):
+        blob = np.frombuffer(b"".join(framed) + (b"\0\0\0\0junk" if end_mark else b""), dtype=np.uint8)
+        dev = torch.device("cuda", 0)
+        d_blob = torch.from_numpy(blob.copy()).to(dev)
+        nmax = len(framed) + 5
+        d_off = torch.zeros(nmax, dtype=torch.int64, device=dev); d_len = torch.zeros(nmax, dtype=torch.int32, device=dev)
+        d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+        sh = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        assert lib.b200lz4_reframe_dev(p(d_blob), blob.size, 8, end_mark, p(d_off), p(d_len), nmax, p(d_res), sh) == 0
+        res = d_res.cpu().numpy()
+        assert res[0] == len(framed) and res[2] == end_mark and res[3] == 0
+        assert res[1] == sum(len(f) for f in framed) + (4 if end_mark else 0)
+        assert d_len[:len(framed)].cpu().tolist() == [len(f) for f in framed]
+        # decode straight from the device-side block table
+        n = len(framed)
+        d_dst_off = torch.from_numpy(offs).to(dev); d_cap = torch.from_numpy(sizes.astype(np.int32)).to(dev)
+        d_out = torch.zeros(total + 64, dtype=torch.uint8, device=dev); d_olen = torch.zeros(n, dtype=torch.int32, device=dev)
+        d_scratch = torch.zeros(lib.b200lz4_scratch_bytes(), dtype=torch.uint8, device=dev)
+        assert lib.b200lz4_decompress_dev(p(d_blob), p(d_off), p(d_len), n, None, 0, None, p(d_out), p(d_dst_off), p(d_cap),
+                                          p(d_olen), 8, 0, p(d_scratch), sh) == 0
+        torch.cuda.synchronize()
+        assert d_olen.cpu().tolist() == [int(s) for s in sizes]
+        assert bytes(d_out[:total].cpu().numpy()) == data.tobytes()
