@@ -196,3 +196,64 @@ def test_corrupted_blocks_accept_reject_like_the_reference(ctx, ref, seed):
                 continue
             raise AssertionError(f"seed {seed} case {note}: gpu {'rejects' if got is None else 'accepts'}, "
                                  f"reference {'rejects' if want is None else 'accepts'}")
+
+
+def _echo_arrays(rng, n_arrays):
+    """Arrays that repeat, shift and lightly edit their predecessors: long matches into the dictionary, matches that run
+    from the dictionary into the current array (the two-segment count, cbits/lz4.c:1080-1089), tiny dictionaries."""
+    from streamly_lz4_b200 import datagen
+    kind = ["text", "records", "random", "mixed"][int(rng.integers(0, 4))]
+    base = datagen.make(kind, int(rng.integers(0, 1 << 30)), int(rng.integers(2000, 90000))).tobytes()
+    out = [base]
+    for _ in range(n_arrays - 1):
+        prev = out[-1]
+        op = int(rng.integers(0, 7))
+        if op == 0:
+            a = prev
+        elif op == 1 and len(prev) > 10:
+            k = int(rng.integers(1, min(len(prev), 5000))); a = prev[k:] + prev[:k]
+        elif op == 2 and len(prev) > 10:
+            b = bytearray(prev)
+            for _ in range(int(rng.integers(1, 20))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            a = bytes(b)
+        elif op == 3:
+            a = prev[-int(rng.integers(1, 70000)):] + prev[:int(rng.integers(0, 70000))]
+        elif op == 4:
+            a = prev[:int(rng.integers(0, 14))]                          # tiny array: a tiny (or dropped) dictionary follows
+        elif op == 5:
+            a = base[:int(rng.integers(1, len(base)))] * int(rng.integers(1, 4))
+        else:
+            a = prev + prev[:int(rng.integers(0, 3000))]
+        out.append(a[:200000])
+    return out
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_echoing_linked_streams_wide_and_dense(ctx, ref, seed):
+    import streamly_lz4_b200 as lz
+    rng = np.random.default_rng(5000 + seed)
+    accel = int(rng.choice([1, 1, 2, 9, 400]))
+    # (i) a handful of streams: the wide kernel (one stream per SM, dictionary in the shared-memory ring)
+    # (ii) more streams than SMs: the dense kernel (dictionary in global memory)
+    for n_streams, per in ((3, 14), (200, 4)):
+        streams = [_echo_arrays(rng, per) for _ in range(n_streams)]
+        arrays = [a for s in streams for a in s]
+        sf = np.zeros(n_streams + 1, dtype=np.int32); sf[1:] = np.cumsum([len(s) for s in streams])
+        lens = np.array([len(a) for a in arrays], dtype=np.int32)
+        strides = (lens.astype(np.int64) + 16 + 15) // 16 * 16
+        offs = np.zeros(len(arrays), dtype=np.int64); offs[1:] = np.cumsum(strides[:-1])
+        src = ctx.pinned("echo_src", int(strides.sum()) + 64)
+        for a, o in zip(arrays, offs):
+            src[o:o + len(a)] = np.frombuffer(a, dtype=np.uint8)
+        dst = ctx.pinned("echo_dst", int((lens.astype(np.int64) + lens // 255 + 24).sum()))
+        rc, doff, olen = ctx.compress_batch(src[:int(strides.sum())], offs, lens, accel, 8, dst, stream_first=sf)
+        assert rc == 0
+        want = ref.compress_chunks(arrays, accel, linked=True, stream_first=sf, threads=8)
+        for i, w in enumerate(want):
+            assert dst[doff[i]:doff[i + 1]].tobytes() == w, f"seed {seed} streams {n_streams} accel {accel} array {i} (len {lens[i]})"
+        back = ctx.pinned("echo_back", int(lens.sum()) + 64)
+        comp = dst[:doff[-1]]
+        rc, boff, blen = ctx.decompress_batch(comp, doff[:-1].copy(), np.diff(doff).astype(np.int32), 8, 0, back, stream_first=sf)
+        assert rc == 0 and (blen == lens).all()
+        assert back[:int(lens.sum())].tobytes() == b"".join(arrays)
