@@ -235,3 +235,18 @@ def test_full_size_config2_checksum(ctx, ref):
     h0 = hashlib.sha256(data.tobytes()).hexdigest()
     h1 = hashlib.sha256(back[:total].tobytes()).hexdigest()
     assert h0 == h1
+
+
+def test_c_example_links_and_round_trips(ctx):
+    """examples/c_roundtrip.c: the C ABI from plain C (gcc, include/b200lz4.h only): batched and legacy interfaces."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "c_roundtrip")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    lib_dir = os.path.join(root, "streamly_lz4_b200")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "c_roundtrip.c"),
+                           "-L" + lib_dir, "-lb200lz4", "-Wl,-rpath," + lib_dir, "-o", exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout
+    assert "batched : " in out.stdout and "legacy  : " in out.stdout
