@@ -178,6 +178,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
@@ -193,6 +194,7 @@ struct BlockIn {
     // wide mode, carried from block to block of a stream: ring position one past the previous array, lowest ring
     // position of contiguously loaded data, and whether both mean anything
     uint32_t w_end, w_lo; bool w_ok;
+    uint32_t tbase;             // compact table: stream position of rel == 1 (carried from block to block)
 };
 
 // Producer side of the queue (finder warp).  The buffer being filled is always already acquired.
@@ -233,7 +235,15 @@ __device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t mask, uint32_t b
 
 // Match finder for one block: pushes sequence descriptors, ends with the final-literals descriptor.
 // data_s (512-byte aligned) / hash_s (1024-byte aligned): shared addresses of this finder's rings.
-template <bool kWide>
+// COMPACT table (kCompact): 16-bit entries plus one epoch bit per bucket, 8.5 KiB instead of 16 KiB, so that more
+// finders fit an SM.  A bucket holds rel = pos - tbase + 1 (17 bits: u16 + the bucket's bit; 0 = empty).  Positions are
+// inserted in non-decreasing order, so when the current position reaches tbase + 131071 every entry in the lower half
+// (rel <= 65536) is more than 65535 behind every future position -- the reference rejects such candidates -- and a
+// SWEEP drops them, moves the upper half down (clear all bits) and advances tbase by 65536.  An empty bucket decodes to
+// tbase - 1, which the distance test rejects by itself.
+constexpr uint32_t kEpoch = 65536u, kRelMax = 2 * kEpoch - 1;       // rel in [1, 131071]
+
+template <bool kWide, bool kCompact>
 __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, const uint32_t hash_s, Producer& out,
                            const uint32_t off0, const uint32_t step0, const uint32_t off1, const uint32_t step1)
 {
@@ -249,6 +259,51 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
     const uint32_t table_s = smem_u32(table);
     int anchor = 0;
     if (kWide && n < kMinLength) in.w_ok = false;       // nothing of a tiny array reaches the ring
+
+    // ---- position table access (classic: u32 per bucket; compact: see above)
+    uint32_t tbase = in.tbase;
+    const uint32_t tfl_s = table_s + 2 * kHashEntries;  // compact: the epoch bits, one u32 per 32 buckets
+    auto t_get = [&](uint32_t h) -> uint32_t {          // stream position held by bucket h
+        if (!kCompact) return lds32(table_s + h * 4);
+        const uint32_t lo = lds16(table_s + h * 2);
+        const uint32_t fw = lds32(tfl_s + ((h >> 5) << 2));
+        return tbase + (lo | (((fw >> (h & 31u)) & 1u) << 16)) - 1u;
+    };
+    auto t_put = [&](uint32_t h, uint32_t pos) {        // warp-uniform insert (every lane stores the same values)
+        if (!kCompact) { sts32(table_s + h * 4, pos); return; }
+        const uint32_t rel = pos - tbase + 1u;
+        sts16(table_s + h * 2, rel & 0xFFFFu);
+        const uint32_t a = tfl_s + ((h >> 5) << 2), bit = 1u << (h & 31u);
+        const uint32_t fw = lds32(a), nw = (rel >> 16) ? (fw | bit) : (fw & ~bit);
+        if (nw != fw) sts32(a, nw);
+    };
+    auto t_put_lane = [&](uint32_t h, uint32_t pos) {   // per-lane insert (distinct buckets in one warp instruction)
+        if (!kCompact) { sts32(table_s + h * 4, pos); return; }
+        const uint32_t rel = pos - tbase + 1u;
+        sts16(table_s + h * 2, rel & 0xFFFFu);
+        uint32_t* w = table + kHashEntries / 2 + (h >> 5);
+        if (rel >> 16) atomicOr(w, 1u << (h & 31u)); else atomicAnd(w, ~(1u << (h & 31u)));
+    };
+    auto t_sweep_to = [&](uint32_t cur) {               // make position cur insertable: rel(cur) <= kRelMax
+        if (!kCompact) return;
+        while (cur - tbase >= kRelMax) {
+            __syncwarp();
+            if (cur - tbase >= 2 * kRelMax) {           // a long skip: everything is stale
+                for (int i = lane; i < kHashEntries / 8; i += 32) sts128(table_s + 16 * i, 0u, 0u, 0u, 0u);
+                for (int i = lane; i < kHashEntries / 32; i += 32) sts32(tfl_s + 4 * i, 0u);
+                tbase = cur - (kEpoch - 1);
+            } else {
+                for (int j = lane; j < kHashEntries / 32; j += 32) {
+                    const uint32_t fw = lds32(tfl_s + 4 * j);
+                    uint32_t clr = ~fw;                 // lower-half entries: out of reach from now on
+                    while (clr) { const int b = __ffs(clr) - 1; clr &= clr - 1; sts16(table_s + 2 * (32 * j + b), 0u); }
+                    sts32(tfl_s + 4 * j, 0u);
+                }
+                tbase += kEpoch;
+            }
+            __syncwarp();
+        }
+    };
 
     if (n >= kMinLength) {
         // ---- window state (see the invariant above)
@@ -504,9 +559,10 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
             const uint32_t h = hash_at(ap);
             const uint32_t cur = S + (uint32_t)p;
             // every lane performs the same accesses in program order: no warp sync needed
-            if (retest) sts32(table_s + hash_at(ap - 2) * 4, cur - 2);                             // :1146
-            const uint32_t m = lds32(table_s + h * 4);
-            sts32(table_s + h * 4, cur);                                                             // :998 / :1185
+            t_sweep_to(cur);
+            if (retest) t_put(hash_at(ap - 2), cur - 2);                                             // :1146
+            const uint32_t m = t_get(h);
+            t_put(h, cur);                                                                           // :998 / :1185
             if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) return false;             // :1001-1006 / :1187-1188
             return verify_count(p, m, retest);
         };
@@ -521,9 +577,10 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
             const uint32_t mine = ring8(ap + lane);             // issued early: overlaps the table chain
             const uint32_t h = hash_at(ap);
             const uint32_t cur = S + (uint32_t)p;
-            sts32(table_s + hash_at(ap - 2) * 4, cur - 2);                                           // :1146
-            const uint32_t m = lds32(table_s + h * 4);
-            sts32(table_s + h * 4, cur);                                                             // :1185
+            t_sweep_to(cur);
+            t_put(hash_at(ap - 2), cur - 2);                                                         // :1146
+            const uint32_t m = t_get(h);
+            t_put(h, cur);                                                                           // :1185
             if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) return false;             // :1187-1188
             const int cpos = (int)(m - S);
             if (m < S && !(kWide && cpos >= lo_pos)) return verify_count(p, m, true);                // candidate in the dictionary, not in the ring
@@ -546,7 +603,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
             return true;
         };
 
-        if (lane == 0) { uint2 v = ldg_5bytes(src); table[hash5(v.x, v.y)] = S; }   // :924
+        { t_sweep_to(S); uint2 v = ldg_5bytes(src); t_put(hash5(v.x, v.y), S); }    // :924
         __syncwarp();
         int ip = 1;                            // :925  (search runs start here)
         bool after_match = false;
@@ -587,7 +644,16 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
                     else probe_schedule(jbase + lane, in.accel, off, step);
                     const long long pos64 = (long long)ip + off;
                     const bool active = lane < width;
-                    const bool valid = active && (pos64 + step <= (long long)mfl);                   // :969
+                    bool valid = active && (pos64 + step <= (long long)mfl);                         // :969
+                    bool clipped = false;               // compact table: probes past the epoch boundary wait for the sweep
+                    if (kCompact) {
+                        // lane 0's position becomes insertable -- only if it is a real probe: sweeping to a position that is
+                        // never reached would break the "positions only grow" rule the sweep relies on
+                        if (__shfl_sync(kFull, (int)valid, 0)) t_sweep_to(S + (uint32_t)__shfl_sync(kFull, (int)pos64, 0));
+                        const bool beyond = valid && ((S + (uint32_t)pos64) - tbase >= kRelMax);
+                        clipped = __ballot_sync(kFull, beyond) != 0;
+                        valid = valid && !beyond;
+                    }
                     uint32_t h = 0, seq = 0, cur = 0;
                     const int pos = valid ? (int)pos64 : 0;
                     if (valid) {
@@ -605,7 +671,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
                     const uint32_t fwd = __shfl_sync(kFull, cur, from_lane);
                     bool ok = false; uint32_t m = 0;
                     if (valid) {
-                        m = lower ? fwd : lds32(table_s + h * 4);
+                        m = lower ? fwd : t_get(h);
                         if (!(dict_small && m < low_index) && (m + kMaxDistance >= cur)) {           // :1001-1006
                             if (kWide && (int)(m - S) >= lo_pos && (int)(m - S) + 4 <= ready_end) {      // (a run may have outrun the loaded lines)
                                 ok = (ring32(g32 + (m - S)) == seq);
@@ -622,7 +688,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
                     const int ncommit = min(w + 1, nvalid);
                     if ((int)lane < ncommit) {                          // ordered commit: last writer per bucket
                         const uint32_t grp = peers & (ncommit >= 32 ? kFull : ((1u << ncommit) - 1u));
-                        if ((31 - __clz(grp)) == (int)lane) sts32(table_s + h * 4, cur);             // :998
+                        if ((31 - __clz(grp)) == (int)lane) t_put_lane(h, cur);                      // :998
                     }
                     __syncwarp();
                     if (w < 32) {
@@ -630,7 +696,10 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
                         mpos = __shfl_sync(kFull, pos, w); midx = __shfl_sync(kFull, m, w);
                         break;
                     }
-                    if (nvalid < (int)width) break;                     // ran into mflimit: last literals
+                    if (nvalid < (int)width) {
+                        if (kCompact && clipped) { jbase += nvalid; continue; }      // the rest of this window after the sweep
+                        break;                                          // ran into mflimit: last literals
+                    }
                     jbase += width;
                     width = 32;
                 }
@@ -676,11 +745,12 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
         cp_async_wait<0>();             // nothing of this block's window may land after the next block starts
         __syncwarp();
     }
+    in.tbase = tbase;
     // last literals, :1204-1231
     out.push((uint32_t)anchor, (uint32_t)(n - anchor), 0u, 0u, in.block);
 }
 
-template <bool kWide>
+template <bool kWide, bool kCompact>
 __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ring, uint16_t* hring, Queue* q)
 {
     const uint32_t lane = lane_id();
@@ -704,18 +774,41 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ri
 
         uint32_t offset = 0, dict_len = 0;
         const uint8_t* dict_end = nullptr;
+        uint32_t tbase = 0;
+        uint16_t* const t16 = reinterpret_cast<uint16_t*>(table);          // compact layout: 4096 x u16, then 128 x u32 epoch bits
+        uint32_t* const tfl = table + kHashEntries / 2;
         {   // table: zero (fresh LZ4_initStream, :1443-1451) or restored
             uint4* t4 = reinterpret_cast<uint4*>(table);
             if (st) {
-                const uint4* g4 = reinterpret_cast<const uint4*>(st->table);
-                for (int i = lane; i < kHashEntries / 4; i += 32) t4[i] = g4[i];
                 offset = st->offset; dict_len = st->dict_len;
                 dict_end = st->dict_buf + dict_len;
+                if (kCompact) {         // positions within reach become rel = pos - tbase + 1 in the lower half, the rest is dropped
+                    // (d == 65535 only for the zero entries of a stream that has not compressed anything yet: position 0 == offset)
+                    tbase = offset - (kEpoch - 1);
+                    for (int k = 0; k < kHashEntries / 32; k++) {
+                        const int i = (int)lane + 32 * k;
+                        const uint32_t d = st->table[i] - tbase;
+                        const uint32_t rel = (d <= kEpoch - 1) ? d + 1u : 0u;
+                        t16[i] = (uint16_t)rel;
+                        const uint32_t hi = __ballot_sync(kFull, (rel >> 16) != 0);
+                        if (lane == 0) tfl[k] = hi;
+                    }
+                } else {
+                    const uint4* g4 = reinterpret_cast<const uint4*>(st->table);
+                    for (int i = lane; i < kHashEntries / 4; i += 32) t4[i] = g4[i];
+                }
+            } else if (kCompact) {      // every bucket = stream position 0 (what a zero-filled table means): rel = 65536
+                tbase = 0u - (kEpoch - 1);
+                for (int i = lane; i < kHashEntries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+                for (int i = lane; i < kHashEntries / 32; i += 32) tfl[i] = 0xFFFFFFFFu;
             } else {
                 for (int i = lane; i < kHashEntries / 4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
             }
             __syncwarp();
         }
+        auto compact_pos = [&](int i) -> uint32_t {     // stream position held by bucket i of the compact table
+            return tbase + ((uint32_t)t16[i] | (((tfl[i >> 5] >> (i & 31)) & 1u) << 16)) - 1u;
+        };
         const uint8_t* last_src = nullptr; int last_n = -1;
         uint32_t w_end = 0, w_lo = 0; bool w_ok = false;
         for (int b = b0; b < b1; b++) {
@@ -724,16 +817,30 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ri
             if (n >= 0 && n <= kMaxInput) {                                                  // :1262
                 if (offset + (uint32_t)n > 0x80000000u) {                                    // LZ4_renormDictT, :1545-1562
                     uint32_t delta = offset - 65536u;
-                    for (int i = lane; i < kHashEntries; i += 32) { uint32_t v = table[i]; table[i] = v < delta ? 0u : v - delta; }
+                    if (kCompact) {     // re-express what is still within reach relative to the new origin (tbase = 1), drop the rest
+                        uint32_t keep[kHashEntries / 32];
+                        #pragma unroll 1
+                        for (int k = 0; k < kHashEntries / 32; k++) {
+                            const uint32_t p = compact_pos(lane + 32 * k);
+                            keep[k] = (offset - p <= kMaxDistance + 1u) ? (p - delta) : 0u;      // new rel = new pos (tbase = 1)
+                        }
+                        __syncwarp();
+                        #pragma unroll 1
+                        for (int k = 0; k < kHashEntries / 32; k++) t16[lane + 32 * k] = (uint16_t)keep[k];
+                        for (int i = lane; i < kHashEntries / 32; i += 32) tfl[i] = 0u;
+                        tbase = 1u;
+                    } else {
+                        for (int i = lane; i < kHashEntries; i += 32) { uint32_t v = table[i]; table[i] = v < delta ? 0u : v - delta; }
+                    }
                     offset = 65536u;
                     if (dict_len > 65536u) dict_len = 65536u;
                     __syncwarp();
                 }
                 if (dict_len >= 1 && dict_len <= 3) dict_len = 0;                            // :1581-1587
-                BlockIn in{src, n, dict_end, dict_len, offset, accel, b, w_end, w_lo, w_ok};
+                BlockIn in{src, n, dict_end, dict_len, offset, accel, b, w_end, w_lo, w_ok, tbase};
                 if (n > 0) offset += (uint32_t)n;                                            // :918 (n == 0 never reaches it, :1263-1273)
-                find_block<kWide>(in, table, data_s, hash_s, out, (uint32_t)off0, (uint32_t)step0, (uint32_t)off1, (uint32_t)step1);
-                w_end = in.w_end; w_lo = in.w_lo; w_ok = in.w_ok;
+                find_block<kWide, kCompact>(in, table, data_s, hash_s, out, (uint32_t)off0, (uint32_t)step0, (uint32_t)off1, (uint32_t)step1);
+                w_end = in.w_end; w_lo = in.w_lo; w_ok = in.w_ok; tbase = in.tbase;
                 __syncwarp();
                 dict_end = src + n; dict_len = (uint32_t)n;                                  // :1633-1634
                 last_src = src; last_n = n;
@@ -744,9 +851,14 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ri
             }
         }
         if (st) {   // persist the stream (what the reference keeps in LZ4_stream_t + the live previous array)
-            uint4* g4 = reinterpret_cast<uint4*>(st->table);
-            const uint4* t4 = reinterpret_cast<const uint4*>(table);
-            for (int i = lane; i < kHashEntries / 4; i += 32) g4[i] = t4[i];
+            if (kCompact) {
+                __syncwarp();
+                for (int i = lane; i < kHashEntries; i += 32) st->table[i] = compact_pos(i);     // (an empty bucket saves as tbase - 1: out of reach for good)
+            } else {
+                uint4* g4 = reinterpret_cast<uint4*>(st->table);
+                const uint4* t4 = reinterpret_cast<const uint4*>(table);
+                for (int i = lane; i < kHashEntries / 4; i += 32) g4[i] = t4[i];
+            }
             if (last_n >= 0) {
                 uint32_t keep = (uint32_t)last_n <= st->dict_cap ? (uint32_t)last_n : 0u;   // host sizes dict_buf; 0 only on misuse
                 if (keep) warp_copy_ro(st->dict_buf, last_src, keep);
@@ -869,9 +981,41 @@ compress_kernel(CompressArgs a)
         mbar_init(&q->empty[0], 1); mbar_init(&q->empty[1], 1);
     }
     __syncthreads();
-    if (warp < kPairs) finder_main<false>(a, tables + pair * kHashEntries, rings + pair * kWinWords, hrings + pair * kHashPos, &queues[pair]);
+    if (warp < kPairs) finder_main<false, false>(a, tables + pair * kHashEntries, rings + pair * kWinWords, hrings + pair * kHashPos, &queues[pair]);
     else emitter_main(a, &queues[pair]);
     // last CTA out resets the work counter so the scratch stays zeroed for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t done = atomicAdd(&a.scratch->work_counter[1], 1u);
+        if (done == gridDim.x - 1) { a.scratch->work_counter[0] = 0; a.scratch->work_counter[1] = 0; __threadfence(); }
+    }
+}
+
+// Compact mode: the dense kernel with 8.5 KiB position tables (see find_block): 4 CTAs of 4 pairs per SM = 16 streams in
+// flight per SM instead of 12.  Used for launches of more than one wave of the classic kernel.
+constexpr int kCompactTableBytes = kHashEntries * 2 + kHashEntries / 8;      // u16 entries + epoch bits
+constexpr size_t kCompactSmem = 1024 /* alignment slack */ + kPairs * (kHashPos * sizeof(uint16_t) + kWinBytes + kCompactTableBytes + sizeof(Queue));
+
+__global__ void __launch_bounds__(kPairs * 64, 4)
+compress_kernel_compact(CompressArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_dyn[];
+    uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint16_t* hrings = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw + kPairs * kHashPos * sizeof(uint16_t));
+    uint8_t* tables = reinterpret_cast<uint8_t*>(rings + kPairs * kWinWords);
+    Queue* queues = reinterpret_cast<Queue*>(tables + kPairs * kCompactTableBytes);
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t pair = warp & (kPairs - 1);
+    if (threadIdx.x < kPairs) {
+        Queue* q = &queues[threadIdx.x];
+        mbar_init(&q->full[0], 1); mbar_init(&q->full[1], 1);
+        mbar_init(&q->empty[0], 1); mbar_init(&q->empty[1], 1);
+    }
+    __syncthreads();
+    if (warp < kPairs) finder_main<false, true>(a, reinterpret_cast<uint32_t*>(tables + pair * kCompactTableBytes), rings + pair * kWinWords,
+                                                 hrings + pair * kHashPos, &queues[pair]);
+    else emitter_main(a, &queues[pair]);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t done = atomicAdd(&a.scratch->work_counter[1], 1u);
@@ -898,7 +1042,7 @@ compress_kernel_wide(CompressArgs a)
         mbar_init(&q->empty[0], 1); mbar_init(&q->empty[1], 1);
     }
     __syncthreads();
-    if (threadIdx.x < 32) finder_main<true>(a, table, ring, hring, q);
+    if (threadIdx.x < 32) finder_main<true, false>(a, table, ring, hring, q);
     else emitter_main(a, q);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -923,6 +1067,8 @@ cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(compress_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(compress_kernel_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCompactSmem);
+        if (e != cudaSuccess) return e;
         sm_counts[dev] = n;
         if (getenv("B200LZ4_DEBUG")) {
             int occ = 0;
@@ -935,6 +1081,13 @@ cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
     static const bool no_wide = getenv("B200LZ4_NO_WIDE") != nullptr;     // A/B switch for measurements
     if (a.n_streams <= sm_count && !no_wide) {   // few streams: one per SM with everything in shared memory
         compress_kernel_wide<<<a.n_streams, 64, kWideSmem, stream>>>(a);
+        return cudaGetLastError();
+    }
+    static const char* compact_env = getenv("B200LZ4_COMPACT");           // A/B switch: "0" never, "1" always (when not wide)
+    const bool compact = compact_env ? (compact_env[0] == '1') : (a.n_streams > sm_count * 3 * kPairs);
+    if (compact) {                               // more than one wave of the classic kernel: 16 streams per SM instead of 12
+        const int max_c = sm_count * 4, want_c = (a.n_streams + kPairs - 1) / kPairs;
+        compress_kernel_compact<<<want_c < max_c ? want_c : max_c, kPairs * 64, kCompactSmem, stream>>>(a);
         return cudaGetLastError();
     }
     const int ctas_per_sm = 3;                   // 3 x (64 KiB of tables + queues) per SM
