@@ -277,6 +277,17 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
         const uint32_t fw = lds32(a), nw = (rel >> 16) ? (fw | bit) : (fw & ~bit);
         if (nw != fw) sts32(a, nw);
     };
+    auto t_swap = [&](uint32_t h, uint32_t pos) -> uint32_t {      // warp-uniform: read bucket h, then insert pos (one flag-word load)
+        if (!kCompact) { const uint32_t m = lds32(table_s + h * 4); sts32(table_s + h * 4, pos); return m; }
+        const uint32_t a = tfl_s + ((h >> 5) << 2), bit = 1u << (h & 31u);
+        const uint32_t lo = lds16(table_s + h * 2);
+        const uint32_t fw = lds32(a);
+        const uint32_t rel = pos - tbase + 1u;
+        sts16(table_s + h * 2, rel & 0xFFFFu);
+        const uint32_t nw = (rel >> 16) ? (fw | bit) : (fw & ~bit);
+        if (nw != fw) sts32(a, nw);
+        return tbase + (lo | ((fw & bit) ? kEpoch : 0u)) - 1u;
+    };
     auto t_put_lane = [&](uint32_t h, uint32_t pos) {   // per-lane insert (distinct buckets in one warp instruction)
         if (!kCompact) { sts32(table_s + h * 4, pos); return; }
         const uint32_t rel = pos - tbase + 1u;
@@ -561,8 +572,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
             // every lane performs the same accesses in program order: no warp sync needed
             t_sweep_to(cur);
             if (retest) t_put(hash_at(ap - 2), cur - 2);                                             // :1146
-            const uint32_t m = t_get(h);
-            t_put(h, cur);                                                                           // :998 / :1185
+            const uint32_t m = t_swap(h, cur);                                                       // :998 / :1185
             if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) return false;             // :1001-1006 / :1187-1188
             return verify_count(p, m, retest);
         };
@@ -579,8 +589,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
             const uint32_t cur = S + (uint32_t)p;
             t_sweep_to(cur);
             t_put(hash_at(ap - 2), cur - 2);                                                         // :1146
-            const uint32_t m = t_get(h);
-            t_put(h, cur);                                                                           // :1185
+            const uint32_t m = t_swap(h, cur);                                                       // :1185
             if ((dict_small && m < low_index) || (m + kMaxDistance < cur)) return false;             // :1187-1188
             const int cpos = (int)(m - S);
             if (m < S && !(kWide && cpos >= lo_pos)) return verify_count(p, m, true);                // candidate in the dictionary, not in the ring
