@@ -1,0 +1,25 @@
+"""The compressor has three kernels (wide: one stream per SM; classic dense; compact-table dense) chosen by the number of
+streams in a launch.  The library reads its A/B switches once per process, so this test re-runs the byte-parity fuzz
+files in child processes with each kernel forced, and checks which kernel actually ran."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SUBSET = ["tests/test_gpu_fuzz.py", "tests/test_gpu_parity.py", "-k",
+          "random_round_trips or echoing or split_over or generators or edge_sizes or acceleration_sweep or linked_state"]
+
+
+@pytest.mark.parametrize("env", [{"B200LZ4_NO_WIDE": "1", "B200LZ4_COMPACT": "1"},      # everything through the compact-table kernel
+                                 {"B200LZ4_NO_WIDE": "1", "B200LZ4_COMPACT": "0"}],     # everything through the classic dense kernel
+                         ids=["compact", "classic"])
+def test_parity_with_forced_kernel(ctx, env):
+    e = dict(os.environ, **env)
+    out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", *SUBSET], cwd=ROOT, env=e,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert " passed" in out.stdout
