@@ -361,3 +361,72 @@ def resize_chunks(cfg: BlockConfig, frame_cfg: FrameConfig, chunks: Iterable) ->
 def decompress_chunks(cfg: BlockConfig, chunks: Iterable, *, ctx: Optional[Context] = None, **kw) -> Iterator[bytes]:
     """decompressChunks (LZ4.hs:114-122) = decompressChunksRawD . resizeChunksD."""
     return decompress_chunks_raw(cfg, resize_chunks(cfg, default_frame_config, chunks), ctx=ctx, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LZ4 frame header, as far as the reference goes (Internal/LZ4.hs:569-651; SURVEY.md section 8f rank 3)
+
+FRAME_MAGIC = 407708164                       # 0x184D2204, little endian on the stream (Internal/LZ4.hs:610)
+_BD_CODES = {4: BlockSize.BlockMax64KB, 5: BlockSize.BlockMax256KB, 6: BlockSize.BlockMax1MB, 7: BlockSize.BlockMax4MB}
+
+
+def simple_frame_parser(header: bytes, *, allow_independent: bool = False):
+    """simpleFrameParserD (Internal/LZ4.hs:590-651) over the 7 header bytes [magic LE32][FLG][BD][HC]:
+    returns (BlockConfig, FrameConfig) with hasEndMark = True; same rejections, same messages.
+    allow_independent: accept the block-independence flag (the reference dies on it, :631-632; this codec supports it)."""
+    if len(header) < 7:
+        raise LZ4Error("simpleFrameParserD: input ended inside the frame header")
+    magic = int.from_bytes(header[0:4], "little")
+    if magic != FRAME_MAGIC:                                                    # :604-620
+        raise LZ4Error(f"The parsed magic {magic} does not match {FRAME_MAGIC}")
+    flg = header[4]
+    if not (not (flg >> 7) & 1 and (flg >> 6) & 1):                            # :624
+        raise LZ4Error("Version is not 01")
+    independent = bool((flg >> 5) & 1)
+    if independent and not allow_independent:
+        raise LZ4Error("Block independence is not yet supported")               # :631-632
+    if (flg >> 4) & 1:
+        raise LZ4Error("Block checksum is not yet supported")
+    if (flg >> 3) & 1:
+        raise LZ4Error("Content size is not yet supported")
+    if (flg >> 2) & 1:
+        raise LZ4Error("Content checksum is not yet supported")
+    if flg & 1:
+        raise LZ4Error("Dict is not yet supported")
+    bs = _BD_CODES.get(header[5] >> 4)                                           # :643-650
+    if bs is None:
+        raise LZ4Error("parseBD: Unknown block max size")
+    return BlockConfig(block_size=bs, independent=independent), FrameConfig(has_end_mark=True)   # header checksum: any byte, :602
+
+
+def frame_header(block_size: BlockSize, *, independent: bool = False) -> bytes:
+    """The 7 bytes benchmark/Main.hs:92-100 writes in front of a framed stream (FLG = version 01, BD = block maximum, HC = 0)."""
+    code = {v: k for k, v in _BD_CODES.items()}[block_size]
+    return FRAME_MAGIC.to_bytes(4, "little") + bytes([0x40 | (0x20 if independent else 0), code << 4, 0])
+
+
+def compress_chunks_frame(cfg: BlockConfig, frame_cfg: FrameConfig, speed: int, chunks: Iterable, **kw) -> Iterator[bytes]:
+    """compressChunksFrame of benchmark/Main.hs:105-118: compressChunksD, then the 4-byte end mark if the frame has one."""
+    yield from compress_chunks(cfg, speed, chunks, **kw)
+    if frame_cfg.has_end_mark:
+        yield b"\x00\x00\x00\x00"
+
+
+def decompress_chunks_with(parser, chunks: Iterable, *, ctx: Optional[Context] = None, **kw) -> Iterator[bytes]:
+    """decompressChunksWithD (Internal/LZ4.hs:569-577): run `parser` over the first 7 bytes of the stream, then
+    decompressChunksRawD cfg . resizeChunksD cfg frameCfg on what follows."""
+    it = iter(chunks)
+    head = b""
+    rest = None
+    for c in it:
+        head += bytes(c)
+        if len(head) >= 7:
+            rest = head[7:]
+            break
+    cfg, frame_cfg = parser(head[:7])
+
+    def tail():
+        if rest:
+            yield rest
+        yield from it
+    return decompress_chunks_raw(cfg, resize_chunks(cfg, frame_cfg, tail()), ctx=ctx, **kw)

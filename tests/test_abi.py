@@ -137,3 +137,27 @@ def test_config_mirror():
     assert c2.meta_size == 4 and c2.max_block_size == 256 * 1024
     assert lz.set_block_independence(True)(cfg).independent
     assert lz.set_frame_end_mark(True)(lz.default_frame_config).has_end_mark
+
+
+def test_frame_header_parser_mirrors_the_reference():
+    """simpleFrameParserD (src/Streamly/Internal/LZ4.hs:590-651): accepted headers, every rejection and its message."""
+    import streamly_lz4_b200 as lz
+    ok = bytes([4, 34, 77, 24, 64, 64, 0])                  # benchmark/Main.hs:92-100
+    cfg, fc = lz.simple_frame_parser(ok)
+    assert cfg.block_size is lz.BlockSize.BlockMax64KB and cfg.meta_size == 4 and fc.has_end_mark and not cfg.independent
+    for code, bs in ((4, "BlockMax64KB"), (5, "BlockMax256KB"), (6, "BlockMax1MB"), (7, "BlockMax4MB")):
+        assert lz.simple_frame_parser(ok[:5] + bytes([code << 4, 0]))[0].block_size is lz.BlockSize[bs]
+        assert lz.frame_header(lz.BlockSize[bs]) == ok[:5] + bytes([code << 4, 0])
+    bad = [(bytes([5, 34, 77, 24, 64, 64, 0]), "does not match 407708164"),
+           (ok[:4] + bytes([0x80, 64, 0]), "Version is not 01"), (ok[:4] + bytes([0x00, 64, 0]), "Version is not 01"),
+           (ok[:4] + bytes([0x60, 64, 0]), "Block independence is not yet supported"),
+           (ok[:4] + bytes([0x50, 64, 0]), "Block checksum is not yet supported"),
+           (ok[:4] + bytes([0x48, 64, 0]), "Content size is not yet supported"),
+           (ok[:4] + bytes([0x44, 64, 0]), "Content checksum is not yet supported"),
+           (ok[:4] + bytes([0x41, 64, 0]), "Dict is not yet supported"),
+           (ok[:5] + bytes([0x30, 0]), "parseBD: Unknown block max size")]
+    for hdr, msg in bad:
+        with pytest.raises(lz.LZ4Error, match=msg):
+            lz.simple_frame_parser(hdr)
+    cfg, _ = lz.simple_frame_parser(ok[:4] + bytes([0x60, 64, 0]), allow_independent=True)
+    assert cfg.independent

@@ -250,3 +250,22 @@ def test_c_example_links_and_round_trips(ctx):
     out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert out.returncode == 0, out.stdout
     assert "batched : " in out.stdout and "legacy  : " in out.stdout
+
+
+def test_framed_stream_with_header_and_end_mark(ctx, ref):
+    """benchmark/Main.hs:85-118 + decompressChunksWithD (Internal/LZ4.hs:569-577): 7-byte frame header, BlockMax64KB blocks
+    (4-byte block headers), 4-byte end mark, junk after it; re-read at several buffer sizes."""
+    import streamly_lz4_b200 as lz
+    from streamly_lz4_b200 import datagen
+    d = datagen.make("text", 91, 1 << 20)
+    arrays = split(d, 65536)
+    hdr = lz.frame_header(lz.BlockSize.BlockMax64KB)
+    cfg, fc = lz.simple_frame_parser(hdr)
+    body = list(lz.compress_chunks_frame(cfg, fc, 65537, arrays, ctx=ctx))
+    assert body[-1] == b"\0\0\0\0"
+    assert body[:-1] == ref.compress_chunks(arrays, 65537, block_size="BlockMax64KB", linked=True)
+    blob = hdr + b"".join(body) + b"trailing bytes after the end mark"
+    for bufsize in (5, 7, 512, 65536, 1 << 20):
+        chunks = [blob[i:i + bufsize] for i in range(0, len(blob), bufsize)]
+        out = b"".join(lz.decompress_chunks_with(lz.simple_frame_parser, chunks, ctx=ctx))
+        assert out == d.tobytes(), f"bufsize {bufsize}"
