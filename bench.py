@@ -253,7 +253,7 @@ def run_gpu(args):
 
     # ---- e2e: the C-ABI host call with pinned host buffers (H2D + kernels + D2H + sync inside)
     ctx = lz.Context(local)
-    pin_src = ctx.pinned("b_src", total)
+    pin_src = ctx.pinned("b_src", total, write_combined=bool(os.environ.get("B200LZ4_BENCH_WC")))
     pin_src[:total] = host
     pin_dst = ctx.pinned("b_dst", int((bound + HEADER).sum()))
     src_view = pin_src[:total]

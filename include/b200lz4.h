@@ -77,6 +77,9 @@ int  b200lz4_ctx_create(int device, b200lz4_ctx** out);
 void b200lz4_ctx_destroy(b200lz4_ctx* ctx);
 /* page-locked host memory for batching arrays (what the Haskell shim copies chunks into) */
 void* b200lz4_host_alloc(size_t bytes);
+/* the same as write-combined memory: for buffers the host only WRITES (batch input): the DMA engine reads them without
+ * cache snooping, which helps when several GPUs pull from one host at once; host READS of such memory are very slow */
+void* b200lz4_host_alloc_wc(size_t bytes);
 void  b200lz4_host_free(void* p);
 
 /* per-call device timings of the last *_batch call on this ctx, milliseconds

@@ -22,6 +22,7 @@ PROTOTYPES = {
     "b200lz4_ctx_create": (c_int, [c_int, ctypes.POINTER(c_vp)]),
     "b200lz4_ctx_destroy": (None, [c_vp]),
     "b200lz4_host_alloc": (c_vp, [c_sz]),
+    "b200lz4_host_alloc_wc": (c_vp, [c_sz]),
     "b200lz4_host_free": (None, [c_vp]),
     "b200lz4_last_timing": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float)] + [ctypes.POINTER(ctypes.c_float)] * 2),
     "b200lz4_launch_count": (c_i64, [c_vp]),

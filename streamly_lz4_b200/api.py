@@ -106,14 +106,14 @@ class Context:
         except Exception:
             pass
 
-    def pinned(self, name: str, nbytes: int) -> np.ndarray:
-        """A reusable page-locked uint8 buffer of at least nbytes."""
+    def pinned(self, name: str, nbytes: int, write_combined: bool = False) -> np.ndarray:
+        """A reusable page-locked uint8 buffer of at least nbytes (write_combined: for input the host only writes)."""
         cur = self._pins.get(name)
         if cur is None or cur[1].size < nbytes:
             if cur is not None:
                 self.lib.b200lz4_host_free(cur[0])
             cap = max(int(nbytes * 1.25) + 4096, 1 << 16)
-            p = self.lib.b200lz4_host_alloc(cap)
+            p = (self.lib.b200lz4_host_alloc_wc if write_combined else self.lib.b200lz4_host_alloc)(cap)
             if not p:
                 raise LZ4Error("b200lz4_host_alloc failed: " + _lib.last_error())
             arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(cap,))

@@ -568,6 +568,13 @@ void* b200lz4_host_alloc(size_t bytes)
     if (e != cudaSuccess) { fail_cuda(e, "cudaMallocHost"); return nullptr; }
     return p;
 }
+void* b200lz4_host_alloc_wc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocWriteCombined | cudaHostAllocPortable);
+    if (e != cudaSuccess) { fail_cuda(e, "cudaHostAlloc(write-combined)"); return nullptr; }
+    return p;
+}
 void b200lz4_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int b200lz4_last_timing(b200lz4_ctx* c, float* h2d, float* kern, float* d2h)
