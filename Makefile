@@ -31,3 +31,10 @@ clean:
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean
+
+# plain-C example over the C ABI (needs a B200 to run)
+examples: $(LIB)
+	mkdir -p build
+	$(CC) -O2 -Wall -Iinclude examples/c_roundtrip.c -L$(PKG) -lb200lz4 -Wl,-rpath,$(CURDIR)/$(PKG) -o build/c_roundtrip
+
+.PHONY: examples
