@@ -12,8 +12,8 @@
 //       * After a match the reference inserts ip-2 and immediately re-tests ip
 //         (cbits/lz4.c:1146-1196).  This "match follows match" regime dominates
 //         compressible data, so it is a warp-uniform scalar path: one broadcast load of
-//         the bytes around ip, two hashes, one table read/write, then ONE 32-lane
-//         load that both verifies the 4-byte candidate and counts the match length.
+//         the bytes around ip, two hashes, one table read/write, then ONE 32-lane byte
+//         compare + ballot that both verifies the candidate and gives the match length.
 //       * Otherwise the serial "probe, overwrite, test" recurrence (cbits/lz4.c:959-1014)
 //         is evaluated up to 32 probes at a time.  Probe positions follow a closed-form
 //         schedule (step_k = (acc*64 + k - 1) >> 6), lane l speculatively evaluates probe
@@ -28,6 +28,15 @@
 //     (mbarrier full/empty handshakes), turns 32 of them at a time into LZ4 sequences:
 //     encoded sizes -> warp prefix sum -> every lane writes its own token / length bytes /
 //     offset, literal runs are copied per lane (short) or cooperatively (long, 128-bit).
+//
+// Three kernels share this code (template parameters of find_block / finder_main), chosen per launch by the number
+// of streams it carries (launch_compress):
+//   compress_kernel          classic: 4 pairs per CTA, 3 CTAs per SM, 16 KiB tables      (up to 12 streams per SM)
+//   compress_kernel_wide     one pair per CTA, one CTA per SM, 128 KiB stream-indexed data ring that also holds the
+//                            dictionary                                                   (no more streams than SMs)
+//   compress_kernel_compact  8.5 KiB tables (16-bit entries + epoch bit, periodic sweeps), 4 CTAs per SM
+//                                                                                        (more than one classic wave)
+// All three produce the reference's bytes; tests/test_gpu_modes.py forces each of them in turn.
 //
 // The compaction pass (compact.cu) then gathers the per-block slots into one stream.
 #include <cstdio>
