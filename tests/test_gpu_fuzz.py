@@ -2,10 +2,14 @@
 (offsets 1..3, long overlapping matches, 255-runs in both length fields, literal runs around the 15/32 limits,
 matches reaching into the previous block), decoded by the GPU and by the oracle; (ii) random arrays / sizes /
 accelerations / linkage through the whole compress -> decompress path against the oracle."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+SHIFT = int(os.environ.get("B200LZ4_FUZZ_SHIFT", "0"))      # soak runs: B200LZ4_FUZZ_SHIFT=1000 python -m pytest tests/test_gpu_fuzz.py
 
 
 def _emit_len(out, v):
@@ -56,7 +60,7 @@ def build_block(rng, target, dict_avail):
 @pytest.mark.parametrize("seed", range(20))
 def test_handbuilt_blocks_decode_like_the_reference(ctx, ref, seed):
     import streamly_lz4_b200 as lz
-    rng = np.random.default_rng(1000 + seed)
+    rng = np.random.default_rng(1000 + seed + SHIFT)
     for linked in (False, True):
         framed = []
         prev = 0
@@ -78,7 +82,7 @@ def test_handbuilt_blocks_decode_like_the_reference(ctx, ref, seed):
 def test_random_round_trips_against_oracle(ctx, ref, seed):
     import streamly_lz4_b200 as lz
     from streamly_lz4_b200 import datagen
-    rng = np.random.default_rng(2000 + seed)
+    rng = np.random.default_rng(2000 + seed + SHIFT)
     kinds = ["text", "random", "sparse01", "records", "mixed", "bits01", "biased01", "zero"]
     for _ in range(12):
         kind = kinds[int(rng.integers(0, len(kinds)))]
@@ -102,7 +106,7 @@ def test_linked_streams_split_over_random_batches(ctx, ref, seed):
     hand-built blocks whose matches reach into the previous output."""
     import streamly_lz4_b200 as lz
     from streamly_lz4_b200 import datagen
-    rng = np.random.default_rng(3000 + seed)
+    rng = np.random.default_rng(3000 + seed + SHIFT)
     kind = ["text", "mixed", "records", "biased01"][seed % 4]
     total = int(rng.integers(200000, 900000))
     data = datagen.make(kind, 40 + seed, total)
@@ -159,7 +163,7 @@ def test_corrupted_blocks_accept_reject_like_the_reference(ctx, ref, seed):
     accept / reject decision as the reference and, when both accept, produce the same bytes."""
     import streamly_lz4_b200 as lz
     from streamly_lz4_b200 import datagen
-    rng = np.random.default_rng(4000 + seed)
+    rng = np.random.default_rng(4000 + seed + SHIFT)
     cfg = lz.BlockConfig(independent=True)
     sources = []
     for target in (64, 400, 5000, 70000):
@@ -232,7 +236,7 @@ def _echo_arrays(rng, n_arrays):
 @pytest.mark.parametrize("seed", range(6))
 def test_echoing_linked_streams_wide_and_dense(ctx, ref, seed):
     import streamly_lz4_b200 as lz
-    rng = np.random.default_rng(5000 + seed)
+    rng = np.random.default_rng(5000 + seed + SHIFT)
     accel = int(rng.choice([1, 1, 2, 9, 400]))
     # (i) a handful of streams: the wide kernel (one stream per SM, dictionary in the shared-memory ring)
     # (ii) more streams than SMs: the dense kernel (dictionary in global memory)
