@@ -32,6 +32,12 @@
  *   - Device buffers handed to the *_dev entry points must be readable up to the
  *     next 16-byte boundary past their last byte (true for any cudaMalloc /
  *     torch allocation).
+ *   - ONE deliberate difference on INVALID input: a match offset of 0 (which the LZ4 block
+ *     format forbids) makes the block fail (out_len < 0).  LZ4 1.9.3's safe decoder accepts
+ *     it and copies bytes of its own not-yet-written output (cbits/lz4.c:2122-2130), so
+ *     the reference "succeeds" with data that depends on what the destination buffer held
+ *     before.  Every other accept/reject decision is the reference's
+ *     (tests/test_gpu_fuzz.py pins both).
  */
 #ifndef B200LZ4_H
 #define B200LZ4_H
@@ -80,6 +86,9 @@ void* b200lz4_host_alloc(size_t bytes);
 /* the same as write-combined memory: for buffers the host only WRITES (batch input): the DMA engine reads them without
  * cache snooping, which helps when several GPUs pull from one host at once; host READS of such memory are very slow */
 void* b200lz4_host_alloc_wc(size_t bytes);
+/* the same from any host thread: selects the ctx's device first (a helper thread that stages the next batch must
+ * not create a CUDA context on device 0 as a side effect) */
+void* b200lz4_ctx_host_alloc(b200lz4_ctx* ctx, size_t bytes);
 void  b200lz4_host_free(void* p);
 
 /* per-call device timings of the last *_batch call on this ctx, milliseconds
@@ -87,6 +96,19 @@ void  b200lz4_host_free(void* p);
 int b200lz4_last_timing(b200lz4_ctx* ctx, float* h2d_ms, float* kernel_ms, float* d2h_ms);
 /* kernels launched by this ctx since creation (codec, scan, gather kernels) */
 int64_t b200lz4_launch_count(b200lz4_ctx* ctx);
+/* text of the last failure of a *_batch call on this ctx, whichever OS thread made it (b200lz4_last_error() is
+ * per calling thread, which an unbound Haskell thread cannot rely on between a `safe` and an `unsafe` call) */
+const char* b200lz4_ctx_last_error(b200lz4_ctx* ctx);
+
+/* Staging helper: copy n separately allocated arrays (pageable memory) to dst + dst_off[i] with `threads` host
+ * threads (0 = a default), one contiguous range of arrays per thread.  This is the gather into page-locked memory
+ * that precedes every batch call when the caller's arrays are not page-locked themselves (Haskell `Array Word8`). */
+int b200lz4_gather_host(void* dst, const void* const* src_ptrs, const int64_t* dst_off, const int32_t* len, int n, int threads);
+
+/* Measurement aid: one plain H2D copy (h2d_bytes from h_src) and one D2H copy (d2h_bytes into h_dst) on the ctx's two
+ * copy streams at once, no kernels, returns when both are complete -- the transfer ceiling an end-to-end call is
+ * compared against (bench.py `e2e.copy_ceiling`). */
+int b200lz4_copy_probe(b200lz4_ctx* ctx, const void* h_src, int64_t h2d_bytes, void* h_dst, int64_t d2h_bytes);
 
 /* -------------------------------------------------- linked-stream state -- */
 /* replaces LZ4_createStream / LZ4_freeStream (cbits/lz4.c:1423-1471) and
@@ -139,6 +161,34 @@ int b200lz4_decompress_batch(b200lz4_ctx* ctx,
                              const int32_t* stream_first, int n_streams, b200lz4_dstream* const* streams,
                              int header_mode, int max_block,
                              void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len);
+
+/* ------------------------------------------- batched, HOST data, N devices -- */
+/* One batch striped over several GPUs of one box: contiguous ranges of blocks (independent
+ * mode) or of whole streams (linked mode), balanced by source bytes; one host thread and one b200lz4_ctx per device;
+ * no exchange step between devices.  Arguments as b200lz4_compress_batch / b200lz4_decompress_batch, except:
+ *   - linked streams start from a fresh state (no persistent stream handles across calls);
+ *   - block i occupies dst[dst_off[i] .. dst_off[i] + header_mode + out_len[i]) (compress) or
+ *     dst[dst_off[i] .. dst_off[i] + out_len[i]) (decompress); blocks are in order, but dst_off[i+1] may lie beyond
+ *     the end of block i where two devices' ranges meet (each device writes into its own worst-case region), so
+ *     dst_cap must be >= the sum of header_mode + b200lz4_compress_bound(src_len[i]) (compress) / of the block
+ *     capacities (decompress).
+ * devices == NULL: the first n usable devices (n <= 0: all). */
+typedef struct b200lz4_mctx b200lz4_mctx;
+int  b200lz4_mctx_create(const int* devices, int n, b200lz4_mctx** out);
+void b200lz4_mctx_destroy(b200lz4_mctx* m);
+int  b200lz4_mctx_size(b200lz4_mctx* m);
+b200lz4_ctx* b200lz4_mctx_ctx(b200lz4_mctx* m, int i);          /* per-device ctx: timings, launch counts */
+const char* b200lz4_mctx_last_error(b200lz4_mctx* m);
+int b200lz4_compress_batch_multi(b200lz4_mctx* m, const void* src, int64_t src_bytes,
+                                 const int64_t* src_off, const int32_t* src_len, int n_blocks,
+                                 const int32_t* stream_first, int n_streams,
+                                 int acceleration, int header_mode,
+                                 void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len);
+int b200lz4_decompress_batch_multi(b200lz4_mctx* m, const void* src, int64_t src_bytes,
+                                   const int64_t* src_off, const int32_t* src_len, int n_blocks,
+                                   const int32_t* stream_first, int n_streams,
+                                   int header_mode, int max_block,
+                                   void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len);
 
 /* --------------------------------------------------- batched, DEVICE data -- */
 /* Everything below takes DEVICE pointers (data and descriptor arrays) and only

@@ -22,10 +22,23 @@ PROTOTYPES = {
     "b200lz4_ctx_create": (c_int, [c_int, ctypes.POINTER(c_vp)]),
     "b200lz4_ctx_destroy": (None, [c_vp]),
     "b200lz4_host_alloc": (c_vp, [c_sz]),
+    "b200lz4_ctx_host_alloc": (c_vp, [c_vp, c_sz]),
     "b200lz4_host_alloc_wc": (c_vp, [c_sz]),
     "b200lz4_host_free": (None, [c_vp]),
     "b200lz4_last_timing": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float)] + [ctypes.POINTER(ctypes.c_float)] * 2),
     "b200lz4_launch_count": (c_i64, [c_vp]),
+    "b200lz4_ctx_last_error": (ctypes.c_char_p, [c_vp]),
+    "b200lz4_gather_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int]),
+    "b200lz4_copy_probe": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64]),
+    "b200lz4_mctx_create": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp)]),
+    "b200lz4_mctx_destroy": (None, [c_vp]),
+    "b200lz4_mctx_size": (c_int, [c_vp]),
+    "b200lz4_mctx_ctx": (c_vp, [c_vp, c_int]),
+    "b200lz4_mctx_last_error": (ctypes.c_char_p, [c_vp]),
+    "b200lz4_compress_batch_multi": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_int,
+                                             c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
+    "b200lz4_decompress_batch_multi": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_int,
+                                               c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
     "b200lz4_cstream_create": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "b200lz4_cstream_free": (None, [c_vp]),
     "b200lz4_dstream_create": (c_int, [c_vp, ctypes.POINTER(c_vp)]),

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes
 import enum
+import threading
 from dataclasses import dataclass, replace
 from typing import Iterable, Iterator, List, Optional, Sequence
 
@@ -113,7 +114,7 @@ class Context:
             if cur is not None:
                 self.lib.b200lz4_host_free(cur[0])
             cap = max(int(nbytes * 1.25) + 4096, 1 << 16)
-            p = (self.lib.b200lz4_host_alloc_wc if write_combined else self.lib.b200lz4_host_alloc)(cap)
+            p = self.lib.b200lz4_host_alloc_wc(cap) if write_combined else self.lib.b200lz4_ctx_host_alloc(self.handle, cap)
             if not p:
                 raise LZ4Error("b200lz4_host_alloc failed: " + _lib.last_error())
             arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(cap,))
@@ -127,6 +128,16 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.b200lz4_launch_count(self.handle))
+
+    def last_error(self) -> str:
+        return self.lib.b200lz4_ctx_last_error(self.handle).decode("utf-8", "replace")
+
+    def copy_probe(self, h_src: np.ndarray, h2d_bytes: int, h_dst: np.ndarray, d2h_bytes: int, check: bool = False) -> int:
+        """One plain H2D + D2H copy pair on the ctx's copy streams (measurement aid, no kernels)."""
+        rc = self.lib.b200lz4_copy_probe(self.handle, h_src.ctypes.data, h2d_bytes, h_dst.ctypes.data, d2h_bytes)
+        if check and rc != 0:
+            raise LZ4Error("b200lz4_copy_probe: " + _lib.last_error())
+        return rc
 
     # ---- raw batch calls on numpy buffers --------------------------------
     def compress_batch(self, src: np.ndarray, src_off: np.ndarray, src_len: np.ndarray,
@@ -220,6 +231,67 @@ class DecompressStream:
             pass
 
 
+class MultiContext:
+    """b200lz4_mctx: one batch striped over several GPUs of the box by one process (host thread + ctx per device)."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, n: int = 0):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        if devices is not None:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self.lib.b200lz4_mctx_create(arr, len(devices), ctypes.byref(h))
+        else:
+            rc = self.lib.b200lz4_mctx_create(None, n, ctypes.byref(h))
+        if rc != 0:
+            raise LZ4Error(f"b200lz4_mctx_create failed ({rc}): {_lib.last_error()}")
+        self.handle = h
+        self.size = int(self.lib.b200lz4_mctx_size(h))
+
+    def close(self):
+        if self.handle:
+            self.lib.b200lz4_mctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_error(self) -> str:
+        return self.lib.b200lz4_mctx_last_error(self.handle).decode("utf-8", "replace")
+
+    def timing(self, i: int):
+        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        self.lib.b200lz4_last_timing(self.lib.b200lz4_mctx_ctx(self.handle, i), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return {"h2d_ms": a.value, "kernel_ms": b.value, "d2h_ms": c.value}
+
+    def launch_count(self) -> int:
+        return sum(int(self.lib.b200lz4_launch_count(self.lib.b200lz4_mctx_ctx(self.handle, i))) for i in range(self.size))
+
+    def compress_batch(self, src, src_off, src_len, accel, header, dst, stream_first=None):
+        n = len(src_len)
+        dst_off = np.zeros(n + 1, dtype=np.int64)
+        out_len = np.zeros(n, dtype=np.int32)
+        sf = None if stream_first is None else np.ascontiguousarray(stream_first, dtype=np.int32)
+        rc = self.lib.b200lz4_compress_batch_multi(
+            self.handle, src.ctypes.data, src.size, src_off.ctypes.data, src_len.ctypes.data, n,
+            None if sf is None else sf.ctypes.data, 0 if sf is None else len(sf) - 1, accel, header,
+            dst.ctypes.data, dst.size, dst_off.ctypes.data, out_len.ctypes.data)
+        return rc, dst_off, out_len
+
+    def decompress_batch(self, src, src_off, src_len, header, max_block, dst, stream_first=None):
+        n = len(src_len)
+        dst_off = np.zeros(n + 1, dtype=np.int64)
+        out_len = np.zeros(n, dtype=np.int32)
+        sf = None if stream_first is None else np.ascontiguousarray(stream_first, dtype=np.int32)
+        rc = self.lib.b200lz4_decompress_batch_multi(
+            self.handle, src.ctypes.data, src.size, src_off.ctypes.data, src_len.ctypes.data, n,
+            None if sf is None else sf.ctypes.data, 0 if sf is None else len(sf) - 1, header, max_block,
+            dst.ctypes.data, dst.size, dst_off.ctypes.data, out_len.ctypes.data)
+        return rc, dst_off, out_len
+
+
 _default_ctx: Optional[Context] = None
 
 
@@ -234,7 +306,7 @@ def _batches(chunks: Iterable, batch_arrays: int, batch_bytes: int):
     group: List[bytes] = []
     size = 0
     for c in chunks:
-        b = c if isinstance(c, (bytes, bytearray, memoryview)) else np.ascontiguousarray(c, dtype=np.uint8).tobytes()
+        b = c if isinstance(c, (bytes, bytearray, memoryview)) else np.ascontiguousarray(c, dtype=np.uint8).reshape(-1)
         group.append(b)
         size += len(b)
         if len(group) >= batch_arrays or size >= batch_bytes:
@@ -244,78 +316,149 @@ def _batches(chunks: Iterable, batch_arrays: int, batch_bytes: int):
         yield group
 
 
-def _gather(ctx: Context, name: str, arrays: Sequence[bytes]):
-    lens = np.array([len(a) for a in arrays], dtype=np.int32)
-    offs = np.zeros(len(arrays), dtype=np.int64)
+def _gather(ctx: Context, name: str, arrays: Sequence):
+    """Lay the arrays of one batch out in a page-locked buffer (b200lz4_gather_host: parallel memcpy in the library)."""
+    n = len(arrays)
+    views = [a if isinstance(a, np.ndarray) else np.frombuffer(a, dtype=np.uint8) for a in arrays]
+    lens = np.fromiter((v.size for v in views), dtype=np.int32, count=n)
+    offs = np.zeros(n, dtype=np.int64)
     # 16-byte aligned starts; a gap keeps consecutive arrays non-adjacent like separate Haskell arrays
     strides = (lens.astype(np.int64) + 16 + 15) // 16 * 16
-    if len(arrays) > 1:
+    if n > 1:
         offs[1:] = np.cumsum(strides[:-1])
     total = int(strides.sum())
     buf = ctx.pinned(name, total)
-    for a, o, n in zip(arrays, offs, lens):
-        if n:
-            buf[o:o + n] = np.frombuffer(a, dtype=np.uint8)
+    ptrs = np.fromiter((v.ctypes.data for v in views), dtype=np.uint64, count=n)
+    rc = ctx.lib.b200lz4_gather_host(buf.ctypes.data, ptrs.ctypes.data, offs.ctypes.data, lens.ctypes.data, n, 0)
+    if rc != 0:
+        raise LZ4Error("b200lz4_gather_host: " + _lib.last_error())
     return buf[:total], offs, lens
 
 
+def _staged(ctx: Context, name: str, groups):
+    """Yield (group, src, offs, lens) with the gather of the NEXT group running on a helper thread while the caller
+    works on the current one (two alternating pinned buffers; ctypes releases the GIL inside the library)."""
+    it = iter(groups)
+    slot = 0
+    box = {}
+
+    def stage(g, k):
+        try:
+            box["out"] = (g,) + _gather(ctx, f"{name}{k}", g)
+        except BaseException as e:      # re-raised on the consumer side
+            box["err"] = e
+
+    def start():
+        nonlocal slot
+        g = next(it, None)
+        if g is None:
+            return None
+        t = threading.Thread(target=stage, args=(g, slot))
+        slot ^= 1
+        t.start()
+        return t
+
+    t = start()
+    while t is not None:
+        t.join()
+        if "err" in box:
+            raise box.pop("err")
+        cur = box.pop("out")
+        t = start()
+        yield cur
+
+
 def compress_chunks(cfg: BlockConfig, speed: int, chunks: Iterable, *, ctx: Optional[Context] = None,
-                    batch_arrays: int = 4096, batch_bytes: int = 256 << 20) -> Iterator[bytes]:
+                    batch_arrays: int = 4096, batch_bytes: int = 256 << 20, copy: bool = True) -> Iterator[bytes]:
     """compressChunks cfg speed (LZ4.hs:94-100): each input array becomes one framed LZ4 block.
 
     Linked mode (default, like the reference): one device stream state for the whole
     stream, arrays strictly in order.  cfg.independent: fresh state per array.
+    copy=False yields numpy views into the pinned result buffer instead of bytes objects (what the Haskell shim does
+    with array slices); a view stays valid until the batch after the next one has been produced.
     """
     ctx = ctx or default_context()
     speed = max(int(speed), 0)                                   # Internal/LZ4.hs:364
     header = cfg.meta_size
     stream = None if cfg.independent else CompressStream(ctx)    # CompressInit, Internal/LZ4.hs:367-376
-    try:
-        for group in _batches(chunks, batch_arrays, batch_bytes):
+
+    def checked(groups):
+        for group in groups:
             for a in group:
                 if len(a) >= 2 * 1024 * 1024 * 1024:             # Internal/LZ4.hs:384-385
                     raise LZ4Error("compressChunksD: Array element > 2 GB encountered")
                 if len(a) > cfg.max_block_size:                  # Internal/LZ4.hs:237-241
                     raise LZ4Error(f"compressChunk: Source array length {len(a)} exceeds the maximum block size "
                                    f"of {cfg.max_block_size}")
-            src, offs, lens = _gather(ctx, "c_src", group)
+            yield group
+    try:
+        k = 0
+        for group, src, offs, lens in _staged(ctx, "c_src", checked(_batches(chunks, batch_arrays, batch_bytes))):
             cap = int((lens.astype(np.int64) + lens // 255 + 16 + header).sum())
-            dst = ctx.pinned("c_dst", cap)
+            dst = ctx.pinned(f"c_dst{k}", cap)
+            k ^= 1
             sf = None if stream is None else np.array([0, len(group)], dtype=np.int32)
             rc, dst_off, out_len = ctx.compress_batch(src, offs, lens, speed, header, dst, sf,
                                                       None if stream is None else [stream])
             if rc != 0:                                          # Internal/LZ4.hs:257-260
-                raise LZ4Error(f"compressChunk: c_compressFastContinue failed ({rc}): {_lib.last_error()}")
+                raise LZ4Error(f"compressChunk: c_compressFastContinue failed ({rc}): {ctx.last_error()}")
             for i in range(len(group)):
-                yield dst[dst_off[i]:dst_off[i + 1]].tobytes()
+                blk = dst[dst_off[i]:dst_off[i + 1]]
+                yield blk.tobytes() if copy else blk
     finally:
         if stream is not None:
             stream.free()                                        # CompressDone, Internal/LZ4.hs:393-394
 
 
+def _decode_batches(chunks: Iterable, batch_arrays: int, batch_bytes: int, cap_of, out_budget: int):
+    """Group framed arrays so that neither the compressed bytes nor the WORST-CASE output of a batch exceed their
+    budgets (BlockMax* headers carry no size: every block may expand to the configured maximum)."""
+    group: List = []
+    size = out = 0
+    for c in chunks:
+        b = c if isinstance(c, (bytes, bytearray, memoryview)) else np.ascontiguousarray(c, dtype=np.uint8).reshape(-1)
+        cap = cap_of(b)
+        if group and (out + cap > out_budget):
+            yield group
+            group, size, out = [], 0, 0
+        group.append(b)
+        size += len(b)
+        out += cap
+        if len(group) >= batch_arrays or size >= batch_bytes:
+            yield group
+            group, size, out = [], 0, 0
+    if group:
+        yield group
+
+
 def decompress_chunks_raw(cfg: BlockConfig, chunks: Iterable, *, ctx: Optional[Context] = None,
-                          batch_arrays: int = 4096, batch_bytes: int = 256 << 20) -> Iterator[bytes]:
-    """decompressChunksRawD (Internal/LZ4.hs:539-567): every input array is exactly one framed block."""
+                          batch_arrays: int = 4096, batch_bytes: int = 256 << 20, out_budget: int = 1 << 30,
+                          copy: bool = True) -> Iterator[bytes]:
+    """decompressChunksRawD (Internal/LZ4.hs:539-567): every input array is exactly one framed block.
+    A batch is flushed as soon as its worst-case output would exceed out_budget bytes (1 GiB)."""
     ctx = ctx or default_context()
     header = cfg.meta_size
     max_block = 0 if cfg.block_size is BlockSize.BlockHasSize else cfg.block_size.value
     stream = None if cfg.independent else DecompressStream(ctx)
+
+    def cap_of(a) -> int:
+        if header == 8:
+            return max(int.from_bytes(bytes(a[4:8]), "little", signed=True), 0) if len(a) >= 8 else 0
+        return max_block + 16
     try:
-        for group in _batches(chunks, batch_arrays, batch_bytes // 2):
-            src, offs, lens = _gather(ctx, "d_src", group)
-            if header == 8:
-                caps = [max(int.from_bytes(a[4:8], "little", signed=True), 0) if len(a) >= 8 else 0 for a in group]
-                cap = int(sum(caps))
-            else:
-                cap = (max_block + 16) * len(group)
-            dst = ctx.pinned("d_dst", cap + 64)
+        k = 0
+        for group, src, offs, lens in _staged(ctx, "d_src", _decode_batches(chunks, batch_arrays, batch_bytes // 2, cap_of, out_budget)):
+            cap = sum(cap_of(a) for a in group)
+            dst = ctx.pinned(f"d_dst{k}", cap + 64)
+            k ^= 1
             sf = None if stream is None else np.array([0, len(group)], dtype=np.int32)
             rc, dst_off, out_len = ctx.decompress_batch(src, offs, lens, header, max_block, dst, sf,
                                                         None if stream is None else [stream])
             if rc != 0:                                          # Internal/LZ4.hs:309-330
-                raise LZ4Error(f"decompressChunk: c_decompressSafeContinue failed ({rc}): {_lib.last_error()}")
+                raise LZ4Error(f"decompressChunk: c_decompressSafeContinue failed ({rc}): {ctx.last_error()}")
             for i in range(len(group)):
-                yield dst[dst_off[i]:dst_off[i] + out_len[i]].tobytes()
+                blk = dst[dst_off[i]:dst_off[i] + out_len[i]]
+                yield blk.tobytes() if copy else blk
     finally:
         if stream is not None:
             stream.free()

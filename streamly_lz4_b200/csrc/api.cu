@@ -10,6 +10,8 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <chrono>
 #include <vector>
 
 #include "b200lz4.h"
@@ -81,6 +83,7 @@ struct b200lz4_ctx {
     cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_k0 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
     int64_t launches = 0;
+    std::string err;                                // text of the last failure of a call on this ctx (any thread)
 };
 
 struct b200lz4_cstream {
@@ -575,6 +578,15 @@ void* b200lz4_host_alloc_wc(size_t bytes)
     if (e != cudaSuccess) { fail_cuda(e, "cudaHostAlloc(write-combined)"); return nullptr; }
     return p;
 }
+void* b200lz4_ctx_host_alloc(b200lz4_ctx* c, size_t bytes)
+{
+    if (!c) { fail(B200LZ4_E_ARG, "ctx is NULL"); return nullptr; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { fail(B200LZ4_E_CUDA, "cudaSetDevice"); return nullptr; }
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { fail_cuda(e, "cudaHostAlloc"); return nullptr; }
+    return p;
+}
 void b200lz4_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int b200lz4_last_timing(b200lz4_ctx* c, float* h2d, float* kern, float* d2h)
@@ -586,6 +598,53 @@ int b200lz4_last_timing(b200lz4_ctx* c, float* h2d, float* kern, float* d2h)
     return 0;
 }
 int64_t b200lz4_launch_count(b200lz4_ctx* c) { return c ? c->launches : 0; }
+const char* b200lz4_ctx_last_error(b200lz4_ctx* c) { return c ? c->err.c_str() : ""; }
+
+// Parallel gather of separately allocated (pageable) arrays into one staging buffer: what the Haskell shim / api.py do
+// before every batch call.  One contiguous range of arrays per thread, balanced by bytes.
+int b200lz4_gather_host(void* dst, const void* const* src_ptrs, const int64_t* dst_off, const int32_t* len, int n, int threads)
+{
+    if (n < 0 || (n > 0 && (!dst || !src_ptrs || !dst_off || !len))) return fail(B200LZ4_E_ARG, "NULL argument");
+    if (n == 0) return 0;
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) { if (len[i] < 0 || (len[i] > 0 && !src_ptrs[i])) return fail(B200LZ4_E_ARG, "bad array"); total += len[i]; }
+    unsigned hw = std::thread::hardware_concurrency();
+    int t = threads > 0 ? threads : (int)(hw ? (hw > 16 ? 16 : hw) : 4);
+    if (total < (int64_t(4) << 20)) t = 1;
+    if (t > n) t = n;
+    auto work = [&](int lo, int hi) {
+        uint8_t* d = static_cast<uint8_t*>(dst);
+        for (int i = lo; i < hi; i++) if (len[i]) memcpy(d + dst_off[i], src_ptrs[i], (size_t)len[i]);
+    };
+    if (t <= 1) { work(0, n); return 0; }
+    std::vector<std::thread> pool;
+    int lo = 0; int64_t done = 0;
+    for (int k = 0; k < t; k++) {
+        const int64_t target = total * (k + 1) / t;
+        int hi = lo;
+        while (hi < n && (done < target || k == t - 1)) done += len[hi++];
+        if (hi > lo) pool.emplace_back(work, lo, hi);
+        lo = hi;
+    }
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
+// Measurement aid (bench.py's copy ceiling): one plain H2D copy of h2d_bytes and one D2H copy of d2h_bytes on the ctx's
+// two copy streams at once, no kernels; returns after both are complete.  Host buffers should be page-locked.
+int b200lz4_copy_probe(b200lz4_ctx* c, const void* h_src, int64_t h2d_bytes, void* h_dst, int64_t d2h_bytes)
+{
+    if (!c || h2d_bytes < 0 || d2h_bytes < 0) return fail(B200LZ4_E_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if (h2d_bytes && (rc = c->d_src.ensure((size_t)h2d_bytes + 64))) return rc;
+    if (d2h_bytes && (rc = c->d_out.ensure((size_t)d2h_bytes + 64))) return rc;
+    if (h2d_bytes) CU(cudaMemcpyAsync(c->d_src.p, h_src, (size_t)h2d_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (d2h_bytes) CU(cudaMemcpyAsync(h_dst, c->d_out.p, (size_t)d2h_bytes, cudaMemcpyDeviceToHost, c->dstream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->dstream));
+    return 0;
+}
 
 int b200lz4_cstream_create(b200lz4_ctx* c, b200lz4_cstream** out)
 {
@@ -648,8 +707,10 @@ int b200lz4_compress_batch(b200lz4_ctx* c, const void* src, int64_t src_bytes,
                            int acceleration, int header_mode,
                            void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
 {
-    return compress_host(c, src, src_bytes, src_off, src_len, n_blocks, stream_first, n_streams, streams,
-                         acceleration, header_mode, nullptr, dst, dst_cap, dst_off, out_len);
+    const int rc = compress_host(c, src, src_bytes, src_off, src_len, n_blocks, stream_first, n_streams, streams,
+                                 acceleration, header_mode, nullptr, dst, dst_cap, dst_off, out_len);
+    if (c && rc) c->err = g_err;
+    return rc;
 }
 
 int b200lz4_decompress_batch(b200lz4_ctx* c, const void* src, int64_t src_bytes,
@@ -658,9 +719,185 @@ int b200lz4_decompress_batch(b200lz4_ctx* c, const void* src, int64_t src_bytes,
                              int header_mode, int max_block,
                              void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
 {
-    return decompress_host(c, src, src_bytes, src_off, src_len, n_blocks, stream_first, n_streams, streams,
-                           header_mode, max_block, dst, dst_cap, dst_off, out_len);
+    const int rc = decompress_host(c, src, src_bytes, src_off, src_len, n_blocks, stream_first, n_streams, streams,
+                                   header_mode, max_block, dst, dst_cap, dst_off, out_len);
+    if (c && rc) c->err = g_err;
+    return rc;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------ several devices
+// One batch striped over the GPUs of one box: contiguous ranges of blocks (independent mode) or of
+// whole streams (linked mode), balanced by source bytes, one host thread and one b200lz4_ctx per device, no exchange step.
+
+struct b200lz4_mctx {
+    std::vector<b200lz4_ctx*> ctx;
+    std::string err;
+};
+
+namespace {
+
+struct Stripe { int u0, u1, b0, b1; };
+
+// contiguous unit ranges with about equal source bytes
+std::vector<Stripe> plan_stripes(const int32_t* len, int n, const int32_t* first, int ns, int parts)
+{
+    const int units = first ? ns : n;
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) total += len[i];
+    std::vector<Stripe> out;
+    int u = 0; int64_t done = 0;
+    for (int k = 0; k < parts; k++) {
+        Stripe s; s.u0 = u; s.b0 = first ? first[u] : u;
+        const int64_t target = total * (k + 1) / parts;
+        while (u < units && (done < target || k == parts - 1)) {
+            const int a = first ? first[u] : u, b = first ? first[u + 1] : u + 1;
+            for (int i = a; i < b; i++) done += len[i];
+            u++;
+        }
+        s.u1 = u; s.b1 = first ? first[u] : u;
+        out.push_back(s);
+    }
+    return out;
+}
+
+template <class Call>
+int run_striped(b200lz4_mctx* m, const int64_t* src_off, const int32_t* src_len, int n,
+                const int32_t* stream_first, int n_streams, const std::vector<int64_t>& region, /* n + 1 prefix of worst-case output */
+                int64_t* dst_off, int32_t* out_len, Call call)
+{
+    const int parts = (int)m->ctx.size();
+    const std::vector<Stripe> st = plan_stripes(src_len, n, stream_first, n_streams, parts);
+    std::vector<int> rcs(parts, 0);
+    std::vector<std::string> errs(parts);
+    std::vector<std::thread> pool;
+    for (int d = 0; d < parts; d++) {
+        const Stripe s = st[d];
+        if (s.b1 <= s.b0) continue;
+        pool.emplace_back([&, d, s]() {
+            const int nb = s.b1 - s.b0;
+            int64_t lo = INT64_MAX, hi = 0;
+            for (int i = s.b0; i < s.b1; i++) { lo = std::min(lo, src_off[i]); hi = std::max(hi, src_off[i] + (int64_t)src_len[i]); }
+            if (lo > hi) lo = hi = 0;
+            std::vector<int64_t> off(nb), doff(nb + 1);
+            for (int i = 0; i < nb; i++) off[i] = src_off[s.b0 + i] - lo;
+            std::vector<int32_t> first;
+            if (stream_first) { first.resize(s.u1 - s.u0 + 1); for (int u = s.u0; u <= s.u1; u++) first[u - s.u0] = stream_first[u] - s.b0; }
+            rcs[d] = call(m->ctx[d], lo, hi - lo, off.data(), src_len + s.b0, nb, stream_first ? first.data() : nullptr, s.u1 - s.u0,
+                          region[s.b0], region[s.b1] - region[s.b0], doff.data(), out_len + s.b0);
+            if (rcs[d]) errs[d] = g_err;
+            if (rcs[d] == 0 || rcs[d] == B200LZ4_E_BLOCK) for (int i = 0; i < nb; i++) dst_off[s.b0 + i] = region[s.b0] + doff[i];
+            if ((rcs[d] == 0 || rcs[d] == B200LZ4_E_BLOCK) && s.b1 == n) dst_off[n] = region[s.b0] + doff[nb];
+        });
+    }
+    for (auto& t : pool) t.join();
+    int rc = 0;
+    for (int d = 0; d < parts; d++) {
+        if (rcs[d] && (rc == 0 || rc == B200LZ4_E_BLOCK)) { rc = rcs[d]; m->err = "device " + std::to_string(m->ctx[d]->device) + ": " + errs[d]; }
+    }
+    if (rc) g_err = m->err;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200lz4_mctx_create(const int* devices, int n, b200lz4_mctx** out)
+{
+    if (!out) return fail(B200LZ4_E_ARG, "out is NULL");
+    *out = nullptr;
+    std::vector<int> devs;
+    if (devices) { if (n <= 0) return fail(B200LZ4_E_ARG, "no devices"); devs.assign(devices, devices + n); }
+    else {
+        int cnt = 0;
+        if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { cudaGetLastError(); return fail(B200LZ4_E_CUDA, "no CUDA device: this library has no CPU path"); }
+        if (n > 0 && n < cnt) cnt = n;
+        for (int d = 0; d < cnt; d++) devs.push_back(d);
+    }
+    b200lz4_mctx* m = new (std::nothrow) b200lz4_mctx();
+    if (!m) return fail(B200LZ4_E_NOMEM, "out of host memory");
+    for (int d : devs) {
+        b200lz4_ctx* c = nullptr;
+        const int rc = b200lz4_ctx_create(d, &c);
+        if (rc) { for (auto* x : m->ctx) b200lz4_ctx_destroy(x); delete m; return rc; }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return 0;
+}
+void b200lz4_mctx_destroy(b200lz4_mctx* m)
+{
+    if (!m) return;
+    for (auto* c : m->ctx) b200lz4_ctx_destroy(c);
+    delete m;
+}
+int b200lz4_mctx_size(b200lz4_mctx* m) { return m ? (int)m->ctx.size() : 0; }
+b200lz4_ctx* b200lz4_mctx_ctx(b200lz4_mctx* m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
+const char* b200lz4_mctx_last_error(b200lz4_mctx* m) { return m ? m->err.c_str() : ""; }
+
+int b200lz4_compress_batch_multi(b200lz4_mctx* m, const void* src, int64_t src_bytes,
+                                 const int64_t* src_off, const int32_t* src_len, int n_blocks,
+                                 const int32_t* stream_first, int n_streams,
+                                 int acceleration, int header_mode,
+                                 void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
+{
+    if (!m || m->ctx.empty()) return fail(B200LZ4_E_ARG, "mctx is NULL");
+    if (n_blocks < 0 || (n_blocks > 0 && (!src_off || !src_len || !dst_off || !out_len || !src || !dst))) return fail(B200LZ4_E_ARG, "NULL argument");
+    if (header_mode != 0 && header_mode != 4 && header_mode != 8) return fail(B200LZ4_E_ARG, "header_mode must be 0, 4 or 8");
+    if (n_blocks == 0) { if (dst_off) dst_off[0] = 0; return 0; }
+    int rc;
+    if ((rc = check_blocks(src_off, src_len, n_blocks, src_bytes))) return rc;
+    if ((rc = check_streams(stream_first, n_streams, n_blocks))) return rc;
+    std::vector<int64_t> region(n_blocks + 1, 0);
+    for (int i = 0; i < n_blocks; i++) region[i + 1] = region[i] + header_mode + bound_of(src_len[i]);
+    if (region[n_blocks] > dst_cap) return fail(B200LZ4_E_NOMEM, "dst_cap too small: need " + std::to_string(region[n_blocks]));
+    const uint8_t* hs = static_cast<const uint8_t*>(src);
+    uint8_t* hd = static_cast<uint8_t*>(dst);
+    return run_striped(m, src_off, src_len, n_blocks, stream_first, n_streams, region, dst_off, out_len,
+        [&](b200lz4_ctx* c, int64_t lo, int64_t bytes, const int64_t* off, const int32_t* len, int nb, const int32_t* first, int ns,
+            int64_t r0, int64_t rcap, int64_t* doff, int32_t* olen) {
+            return compress_host(c, hs + lo, bytes, off, len, nb, first, ns, nullptr, acceleration, header_mode, nullptr,
+                                 hd + r0, rcap, doff, olen);
+        });
+}
+
+int b200lz4_decompress_batch_multi(b200lz4_mctx* m, const void* src, int64_t src_bytes,
+                                   const int64_t* src_off, const int32_t* src_len, int n_blocks,
+                                   const int32_t* stream_first, int n_streams,
+                                   int header_mode, int max_block,
+                                   void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
+{
+    if (!m || m->ctx.empty()) return fail(B200LZ4_E_ARG, "mctx is NULL");
+    if (n_blocks < 0 || (n_blocks > 0 && (!src_off || !src_len || !dst_off || !out_len || !src || !dst))) return fail(B200LZ4_E_ARG, "NULL argument");
+    if (header_mode != 0 && header_mode != 4 && header_mode != 8) return fail(B200LZ4_E_ARG, "header_mode must be 0, 4 or 8");
+    if (header_mode != 8 && max_block < 0) return fail(B200LZ4_E_ARG, "max_block");
+    if (n_blocks == 0) { if (dst_off) dst_off[0] = 0; return 0; }
+    int rc;
+    if ((rc = check_blocks(src_off, src_len, n_blocks, src_bytes))) return rc;
+    if ((rc = check_streams(stream_first, n_streams, n_blocks))) return rc;
+    const uint8_t* hs = static_cast<const uint8_t*>(src);
+    uint8_t* hd = static_cast<uint8_t*>(dst);
+    std::vector<int64_t> region(n_blocks + 1, 0);
+    for (int i = 0; i < n_blocks; i++) {
+        int cap = max_block;
+        if (header_mode == 8) cap = src_len[i] >= 8 ? le32(hs + src_off[i] + 4) : 0;
+        if (cap < 0) cap = 0;
+        region[i + 1] = region[i] + (header_mode == 8 ? (int64_t)cap : align16((int64_t)cap));
+    }
+    if (region[n_blocks] > dst_cap) return fail(B200LZ4_E_NOMEM, "dst_cap too small: need " + std::to_string(region[n_blocks]));
+    return run_striped(m, src_off, src_len, n_blocks, stream_first, n_streams, region, dst_off, out_len,
+        [&](b200lz4_ctx* c, int64_t lo, int64_t bytes, const int64_t* off, const int32_t* len, int nb, const int32_t* first, int ns,
+            int64_t r0, int64_t rcap, int64_t* doff, int32_t* olen) {
+            return decompress_host(c, hs + lo, bytes, off, len, nb, first, ns, nullptr, header_mode, max_block,
+                                   hd + r0, rcap, doff, olen);
+        });
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---------------------------------------------------------------- device path
 

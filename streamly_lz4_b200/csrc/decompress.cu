@@ -25,6 +25,7 @@
 //                copied by all lanes (overlapping matches are a periodic source);
 //       bulk     sequences with a long literal run or a long match travel alone and are
 //                copied cooperatively global -> global.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -498,7 +499,10 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
         const int stream = q->stream[b];
         uint8_t* const dst = C.dst;
 
-        if (cf & kBulk) {
+        if (a.debug & 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q->empty[b]);
+        } else if (cf & kBulk) {
             // ---- one long sequence, copied cooperatively global -> global
             __syncwarp();
             if (lane == 0) mbar_arrive(&q->empty[b]);
@@ -692,7 +696,10 @@ cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream)
     if (a.n_streams <= 0) return cudaSuccess;
     const int max_ctas = sm_count * 16;
     const int grid = a.n_streams < max_ctas ? a.n_streams : max_ctas;
-    decompress_kernel<<<grid, 64, 0, stream>>>(a);
+    static const char* dbg = getenv("B200LZ4_DECODE_DEBUG");
+    DecompressArgs b = a;
+    b.debug = dbg ? atoi(dbg) : 0;
+    decompress_kernel<<<grid, 64, 0, stream>>>(b);
     return cudaGetLastError();
 }
 

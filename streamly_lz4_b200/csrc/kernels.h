@@ -22,6 +22,7 @@ struct DecompressArgs {
     uint8_t* dst; const int64_t* dst_off; const int32_t* dst_cap; int32_t* out_len;
     int header; int max_block;
     Scratch* scratch;
+    int debug;                  // measurement switches (B200LZ4_DECODE_DEBUG): 1 = copier skips every copy (parser-bound rate)
 };
 
 struct CompactArgs {

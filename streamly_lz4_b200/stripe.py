@@ -36,24 +36,40 @@ def stripe_streams(stream_first: Optional[np.ndarray], n_blocks: int, rank: int,
     return b_lo, b_hi, (sf[s_lo:s_hi + 1] - b_lo).astype(np.int32)
 
 
-def gather_lengths(local_lens: np.ndarray, n_total: int, rank: int, world: int, device=None) -> np.ndarray:
+def gather_lengths(local_lens: np.ndarray, n_total: int, rank: int, world: int, device=None,
+                   block_range: Optional[Tuple[int, int]] = None) -> np.ndarray:
     """All ranks' per-block output lengths in global block order (int32[n_total]).
 
-    Stripes are the contiguous ranges of stripe_range(), so a padded all_gather is enough."""
+    block_range = (lo, hi): the global block indices this rank owns.  Default: stripe_range(n_total, rank, world), the
+    independent-blocks stripe; linked streams (stripe_streams) own uneven block ranges and MUST pass theirs.  The
+    ranges of all ranks are exchanged first, so a mismatch between len(local_lens) and the owned range is an error
+    instead of lengths landing at the wrong block indices."""
     local = np.ascontiguousarray(local_lens, dtype=np.int32)
+    lo, hi = block_range if block_range is not None else stripe_range(n_total, rank, world)
+    if hi - lo != len(local):
+        raise ValueError(f"rank {rank} owns blocks [{lo}, {hi}) but reports {len(local)} lengths")
     if world == 1:
+        if (lo, hi) != (0, n_total):
+            raise ValueError("a single rank must own every block")
         return local.copy()
     import torch
     import torch.distributed as dist
-    width = max(stripe_range(n_total, r, world)[1] - stripe_range(n_total, r, world)[0] for r in range(world))
+    r_t = torch.tensor([lo, hi], dtype=torch.int64, device=device)
+    r_all = [torch.zeros_like(r_t) for _ in range(world)]
+    dist.all_gather(r_all, r_t)
+    ranges = [(int(t[0]), int(t[1])) for t in r_all]
+    width = max(max(b - a for a, b in ranges), 1)
     t = torch.zeros(width, dtype=torch.int32, device=device)
     t[:len(local)] = torch.from_numpy(local).to(t.device)
     parts = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(parts, t)
     out = np.zeros(n_total, dtype=np.int32)
-    for r, p in enumerate(parts):
-        lo, hi = stripe_range(n_total, r, world)
-        out[lo:hi] = p[:hi - lo].cpu().numpy()
+    covered = 0
+    for (a, b), p in zip(ranges, parts):
+        out[a:b] = p[:b - a].cpu().numpy()
+        covered += b - a
+    if covered != n_total:
+        raise ValueError(f"ranks cover {covered} of {n_total} blocks")
     return out
 
 

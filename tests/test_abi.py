@@ -161,3 +161,22 @@ def test_frame_header_parser_mirrors_the_reference():
             lz.simple_frame_parser(hdr)
     cfg, _ = lz.simple_frame_parser(ok[:4] + bytes([0x60, 64, 0]), allow_independent=True)
     assert cfg.independent
+
+
+def test_gather_host_is_a_parallel_memcpy(built):
+    """b200lz4_gather_host is plain host code (the staging step in front of every batch call): usable without a GPU."""
+    import ctypes
+    from streamly_lz4_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    arrays = [rng.integers(0, 256, int(k), dtype=np.uint8) for k in rng.integers(0, 400000, 57)]
+    lens = np.array([a.size for a in arrays], dtype=np.int32)
+    offs = np.zeros(len(arrays), dtype=np.int64)
+    offs[1:] = np.cumsum((lens[:-1].astype(np.int64) + 31) // 16 * 16)
+    dst = np.zeros(int(offs[-1] + lens[-1] + 64), dtype=np.uint8)
+    ptrs = np.array([a.ctypes.data for a in arrays], dtype=np.uint64)
+    for threads in (1, 0, 5):
+        dst[:] = 0
+        assert lib.b200lz4_gather_host(dst.ctypes.data, ptrs.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(arrays), threads) == 0
+        for a, o in zip(arrays, offs):
+            assert np.array_equal(dst[o:o + a.size], a)

@@ -123,10 +123,11 @@ def test_large_blocks_4mib(ctx, ref):
     check_roundtrip(lz, ctx, ref, split(d, 4 << 20), 1, True)
 
 
-def test_linked_state_persists_across_batches(ctx, ref):
+def test_linked_state_persists_across_batches(ctx, ref, port):
     """One Haskell stream == one LZ4_stream_t across ALL arrays (Internal/LZ4.hs:367-394): splitting the
     stream into several library calls must not change a byte, and the device hash table must equal the
     oracle's after every call (the table is observable state)."""
+    import ctypes
     import streamly_lz4_b200 as lz
     from streamly_lz4_b200 import datagen
     d = datagen.make("text", 77, 40 * 30000)
@@ -137,6 +138,37 @@ def test_linked_state_persists_across_batches(ctx, ref):
         assert got == want, f"batch_arrays={batch_arrays}"
         back = list(lz.decompress_chunks_raw(lz.BlockConfig(), want, ctx=ctx, batch_arrays=batch_arrays))
         assert back == arrays
+
+    # the state itself: drive one device stream and one oracle stream (the restatement exposes its table) call by
+    # call and compare currentOffset and every table entry that can still produce a candidate (within 65535 of it)
+    lib = port.lib
+    lib.ora_cstream_table.restype = ctypes.POINTER(ctypes.c_uint32); lib.ora_cstream_table.argtypes = [ctypes.c_void_p]
+    lib.ora_cstream_offset.restype = ctypes.c_uint32; lib.ora_cstream_offset.argtypes = [ctypes.c_void_p]
+    arena, ptrs, lens = port.lay_out(arrays)
+    ocs = port.ccreate()
+    cs = lz.CompressStream(ctx)
+    dstbuf = np.zeros(40000, dtype=np.uint8)
+    per_call = 3
+    try:
+        for c0 in range(0, len(arrays), per_call):
+            group = arrays[c0:c0 + per_call]
+            src, offs, glens = lz.api._gather(ctx, "t_src", group)
+            dst = ctx.pinned("t_dst", int((glens.astype(np.int64) + glens // 255 + 24).sum()))
+            rc, doff, olen = ctx.compress_batch(src, offs, glens, 1, 8, dst, np.array([0, len(group)], dtype=np.int32), [cs])
+            assert rc == 0
+            for i in range(c0, c0 + len(group)):
+                r = port.ccont(ocs, int(ptrs[i]), dstbuf.ctypes.data, int(lens[i]), dstbuf.size, 1)
+                assert r > 0 and dst[doff[i - c0] + 8:doff[i - c0 + 1]].tobytes() == dstbuf[:r].tobytes()
+            table, off = cs.peek()
+            want_off = int(lib.ora_cstream_offset(ocs))
+            want_table = np.ctypeslib.as_array(lib.ora_cstream_table(ocs), shape=(4096,)).copy()
+            assert off == want_off
+            live = (want_table.astype(np.int64) + 65535 >= want_off) | (table.astype(np.int64) + 65535 >= off)
+            assert np.array_equal(table[live], want_table[live]), f"device table differs from the oracle's after array {c0 + len(group)}"
+            assert live.sum() > 1000
+    finally:
+        cs.free()
+        port.cfree(ocs)
 
 
 def test_fragmented_stream_decompress(ctx, ref):

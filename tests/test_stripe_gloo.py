@@ -28,16 +28,8 @@ def _worker(rank, world, port, linked, q):
         lo, hi, local_sf = stripe.stripe_streams(sf, n, rank, world)
         mine = ora.compress_chunks(arrays[lo:hi], 3, linked=linked, stream_first=local_sf)
         lens = np.array([len(m) - 8 for m in mine], dtype=np.int32)
-        # independent blocks stripe by block range, so a padded all_gather works; streams stripe unevenly
-        if linked:
-            import torch
-            parts = [None] * world
-            dist.all_gather_object(parts, (lo, hi, lens))
-            all_lens = np.zeros(n, dtype=np.int32)
-            for l, h, v in parts:
-                all_lens[l:h] = v
-        else:
-            all_lens = stripe.gather_lengths(lens, n, rank, world)
+        # independent blocks own stripe_range(); linked streams own uneven block ranges and say so
+        all_lens = stripe.gather_lengths(lens, n, rank, world, block_range=(lo, hi) if linked else None)
         off = stripe.global_offsets(all_lens, 8)
         blob = [None] * world
         dist.all_gather_object(blob, b"".join(mine))

@@ -1,5 +1,5 @@
 import os, sys, time, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import streamly_lz4_b200 as lz
 from streamly_lz4_b200 import datagen
 total=1<<30; BLOCK=640000
