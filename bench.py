@@ -438,7 +438,7 @@ def run_gpu(args):
     e2e_launches = ctx.launch_count() - launches0          # counted by the library: chunks x (codec + scan + gather)
     assert rc == 0 and int(doff[-1]) == comp_total
     clocks = sampler.stop() if rank == 0 else None
-    ceiling = copy_ceiling(ctx, pin_src, total, pin_dst, comp_total, 5, barrier)
+    ceiling = copy_ceiling(ctx, pin_src, total, ctx.pinned("b_probe", comp_total), comp_total, 5, barrier)
 
     # ---- e2e_staged: the public array API from pageable per-array buffers (gather into pinned memory inside)
     staged = None

@@ -77,7 +77,7 @@ struct b200lz4_ctx {
     cudaStream_t kstream[kKernelStreams] = {};      // chunk kernels (run concurrently)
     cudaStream_t dstream = nullptr;                 // D2H
     Scratch* scratch = nullptr;                     // kMaxChunks records: one work counter per in-flight kernel
-    DevBuf d_src, d_slots, d_out, d_desc;
+    DevBuf d_src, d_slots, d_out, d_desc, d_wide;   // d_wide: descriptor rings of decompress_kernel_wide (one slice per chunk)
     PinBuf h_desc;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_k0 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
@@ -406,6 +406,13 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     if ((rc = c->d_src.ensure((size_t)src_bytes + 64))) return rc;
     if ((rc = c->d_slots.ensure((size_t)slots_total + 64))) return rc;
     if (!contiguous && (rc = c->d_out.ensure((size_t)slots_total + 64))) return rc;
+    // descriptor rings for chunks the wide kernel may take (few streams): one slice of one CTA-arena per stream, per chunk
+    int wide_first[kMaxChunks + 1] = {0};
+    for (int k = 0; k < nchunks; k++) {
+        const int nsk = chunks[k].s1 - chunks[k].s0;
+        wide_first[k + 1] = wide_first[k] + (nsk < kWideMaxCtas ? nsk : kWideMaxCtas);
+    }
+    if ((rc = c->d_wide.ensure((size_t)wide_first[nchunks] * kWideArenaPerCta))) return rc;
     uint8_t* d_src = static_cast<uint8_t*>(c->d_src.p);
     uint8_t* d_slots = static_cast<uint8_t*>(c->d_slots.p);
     uint8_t* d_out = static_cast<uint8_t*>(c->d_out.p);
@@ -437,6 +444,8 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
         a.dst_cap = reinterpret_cast<const int32_t*>(dd + o_cap);
         a.out_len = d_out_len;
         a.header = header; a.max_block = max_block; a.scratch = c->scratch + k;
+        a.wide_arena = reinterpret_cast<uint4*>(static_cast<uint8_t*>(c->d_wide.p) + (size_t)wide_first[k] * kWideArenaPerCta);
+        a.wide_ctas = wide_first[k + 1] - wide_first[k];
         CU(launch_decompress(a, ks));
         c->launches += kernel_launches_per_decompress();
         const int nk = ch.b1 - ch.b0;
@@ -550,7 +559,7 @@ void b200lz4_ctx_destroy(b200lz4_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    c->d_src.release(); c->d_slots.release(); c->d_out.release(); c->d_desc.release(); c->h_desc.release();
+    c->d_src.release(); c->d_slots.release(); c->d_out.release(); c->d_desc.release(); c->d_wide.release(); c->h_desc.release();
     if (c->scratch) cudaFree(c->scratch);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_h2d) if (e) cudaEventDestroy(e);
@@ -903,7 +912,7 @@ extern "C" {
 
 size_t b200lz4_cstate_bytes(void) { return sizeof(CState); }
 size_t b200lz4_dstate_bytes(void) { return sizeof(DState); }
-size_t b200lz4_scratch_bytes(void) { return sizeof(Scratch); }
+size_t b200lz4_scratch_bytes(void) { return kScratchBytes; }
 
 int b200lz4_cstate_set_dict(void* d_state, void* d_dict_buf, uint32_t dict_cap, void* cuda_stream)
 {
@@ -942,6 +951,7 @@ int b200lz4_decompress_dev(const void* d_src, const int64_t* d_src_off, const in
     a.stream_first = d_stream_first; a.n_streams = d_stream_first ? n_streams : n_blocks; a.states = d_states;
     a.dst = static_cast<uint8_t*>(d_dst); a.dst_off = d_dst_off; a.dst_cap = d_dst_cap; a.out_len = d_out_len;
     a.header = header_mode; a.max_block = max_block; a.scratch = static_cast<Scratch*>(d_scratch);
+    a.wide_arena = reinterpret_cast<uint4*>(static_cast<uint8_t*>(d_scratch) + sizeof(Scratch)); a.wide_ctas = kWideMaxCtas;
     CU(launch_decompress(a, static_cast<cudaStream_t>(cuda_stream)));
     return 0;
 }

@@ -115,13 +115,8 @@ cudaError_t launch_reframe(const uint8_t* buf, int64_t len, int header, int has_
 
 cudaError_t launch_compact(const CompactArgs& a, cudaStream_t stream)
 {
-    static int sm_counts[64] = {0};     // per device
-    int dev = 0; cudaError_t e0 = cudaGetDevice(&dev); if (e0 != cudaSuccess) return e0;
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (!sm_counts[dev]) {
-        e0 = cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev); if (e0 != cudaSuccess) return e0;
-    }
-    const int sm_count = sm_counts[dev];
+    int sm_count = 0;
+    cudaError_t e0 = device_sm_count(&sm_count); if (e0 != cudaSuccess) return e0;
     scan_kernel<<<1, kScanThreads, 0, stream>>>(a.len, a.n_blocks, a.header, a.out_off, a.host_off, a.host_len);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || a.n_blocks <= 0) return e;

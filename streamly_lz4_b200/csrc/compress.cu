@@ -41,6 +41,7 @@
 // The compaction pass (compact.cu) then gathers the per-block slots into one stream.
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -1073,28 +1074,30 @@ compress_kernel_wide(CompressArgs a)
 
 cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
 {
-    static int sm_counts[64] = {0};     // per device: SM count, 0 = kernel not configured there yet
+    static std::mutex mu;
+    static bool configured[64] = {false};   // per device: dynamic shared-memory limits of the three kernels set
     const size_t smem = kPairs * kHashEntries * sizeof(uint32_t) + kPairs * sizeof(Queue) + kPairs * kWinWords * sizeof(uint32_t)
                         + kPairs * kHashPos * sizeof(uint16_t) + 1024 /* alignment slack */;
-    int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (!sm_counts[dev]) {
-        int n = 0;
-        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(compress_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(compress_kernel_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCompactSmem);
-        if (e != cudaSuccess) return e;
-        sm_counts[dev] = n;
-        if (getenv("B200LZ4_DEBUG")) {
-            int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, compress_kernel, kPairs * 64, smem);
-            fprintf(stderr, "[b200lz4] compress_kernel: %zu B dynamic smem, %d CTAs/SM, %d SMs\n", smem, occ, n);
+    int sm_count = 0;
+    cudaError_t e = device_sm_count(&sm_count); if (e != cudaSuccess) return e;
+    int dev = 0; e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!configured[dev]) {
+            e = cudaFuncSetAttribute(compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(compress_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(compress_kernel_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCompactSmem);
+            if (e != cudaSuccess) return e;
+            configured[dev] = true;
+            if (getenv("B200LZ4_DEBUG")) {
+                int occ = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, compress_kernel, kPairs * 64, smem);
+                fprintf(stderr, "[b200lz4] compress_kernel: %zu B dynamic smem, %d CTAs/SM, %d SMs\n", smem, occ, sm_count);
+            }
         }
     }
-    const int sm_count = sm_counts[dev];
     if (a.n_streams <= 0) return cudaSuccess;
     static const bool no_wide = getenv("B200LZ4_NO_WIDE") != nullptr;     // A/B switch for measurements
     if (a.n_streams <= sm_count && !no_wide) {   // few streams: one per SM with everything in shared memory

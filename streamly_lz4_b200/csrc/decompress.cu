@@ -26,30 +26,14 @@
 //       bulk     sequences with a long literal run or a long match travel alone and are
 //                copied cooperatively global -> global.
 #include <cstdlib>
-#include "common.cuh"
-#include "kernels.h"
+#include <mutex>
+#include "decode_common.cuh"
 
 namespace b200lz4 {
 
+using namespace dec;
+
 namespace {
-
-constexpr int kInRing = 4096;            // bytes of compressed payload resident in shared memory
-constexpr int kFill = 512;               // ring fill unit (32 lanes x 16 bytes)
-constexpr int kOutRing = 8192;           // bytes of recent output resident in shared memory
-constexpr int kQDepth = 32;              // descriptors per queue buffer
-constexpr uint32_t kShortLit = 32;       // sequences within these limits take the lane-parallel path
-constexpr uint32_t kShortMatch = 64;
-constexpr int kWindowSeqs = 11;          // most sequences one 32-byte parse window can hold (3 bytes each)
-// A batch is at most kQDepth short sequences: <= 32 * (1 + 32 + 2 + 1) = 1152 compressed bytes (plus skipped
-// length bytes, which nobody reads again) and <= 32 * (32 + 64) = 3072 output bytes.
-
-constexpr int kCountMask = 0xFFFF;
-constexpr int kBulk = 1 << 16;           // the batch is one sequence to be copied cooperatively
-constexpr int kBegin = 1 << 17;          // first batch of a block
-constexpr int kStreamBegin = 1 << 18;    // ... of the first block of a stream
-constexpr int kStreamEnd = 1 << 19;      // with kEndBlock: last block of the stream
-constexpr int kEndBlock = 1 << 30;       // block finished; result[] holds what to report
-constexpr int kTerminate = 1 << 29;
 
 struct __align__(16) DQueue {
     uint4 desc[2][kQDepth];              // short: {literal start (ring space), lit | mlen << 8 | offset << 16, output position, -}
@@ -61,60 +45,11 @@ struct __align__(16) DQueue {
     int result[2];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ uint4 lds128(uint32_t a)
-{ uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
-{ asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
-__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* g)
-{ asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
-{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
-{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
-}
-
-__device__ __forceinline__ int read_le32(const uint8_t* p)
-{ return (int)((uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24)); }
-
-// Header fields and the checks of decompressChunk (src/Streamly/Internal/LZ4.hs:303-318): both warps
-// derive the same block geometry from the descriptor arrays.
-struct BlockGeom { const uint8_t* payload; int comp_len; int cap; uint8_t* out; bool ok; };
-__device__ __forceinline__ BlockGeom block_geom(const DecompressArgs& a, int b)
-{
-    BlockGeom g;
-    const uint8_t* arr = a.src + a.src_off[b];
-    const int avail = a.src_len[b] - a.header;
-    g.payload = arr + a.header; g.out = a.dst + a.dst_off[b];
-    g.comp_len = 0; g.cap = 0; g.ok = false;
-    if (avail >= 0) {
-        g.comp_len = a.header >= 4 ? read_le32(arr) : avail;                  // LZ4.hs:303
-        g.cap = a.header == 8 ? read_le32(arr + 4) : a.max_block;             // LZ4.hs:189-198
-        g.ok = g.comp_len > 0 && g.comp_len == avail && g.cap >= 0;           // LZ4.hs:309-318 (array length bounds the read)
-        if (a.dst_cap && g.cap > a.dst_cap[b]) g.ok = false;
-    }
-    return g;
-}
-
 // ------------------------------------------------------------------ parser ----
 
 struct Parser {
+    static constexpr bool kWide = false;
+    static constexpr int kRing = kInRing;
     DQueue* q;
     uint32_t ring_s;            // shared address of the input ring
     // queue producer state
@@ -155,12 +90,19 @@ struct Parser {
         begin();                        // the buffer of the batch before the one just published is now free ...
         // ... so only the batch just published can still be pending
     }
-    __device__ __forceinline__ void push(uint32_t lit_src, uint32_t lit, uint32_t mlen, uint32_t off)
+    __device__ __forceinline__ void push(uint32_t lit_src, uint32_t lit, uint32_t mlen, uint32_t off, int /*op_after*/ = 0)
     {
         if (lane_id() == 0) sts128(slot_s, lit_src, lit, mlen, off);
         slot_s += 16;
         fill++;
     }
+    // window path: lane-parallel descriptor stores, then the batch grows by n
+    __device__ __forceinline__ void put(uint32_t rank, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { sts128(slot_s + 16u * rank, x, y, z, w); }
+    __device__ __forceinline__ void advance(int n, int /*op_after*/) { slot_s += 16u * (uint32_t)n; fill += n; }
+    // a long sequence travels alone
+    __device__ __forceinline__ void push_bulk(uint32_t lit_src, uint32_t lit, uint32_t mlen, uint32_t off, int /*op_seq*/, int ip_after)
+    { push(lit_src, lit, mlen, off); publish(kBulk, 0, ip_after); }
+    __device__ __forceinline__ void note_reach(int) {}
     __device__ __forceinline__ uint32_t at(int p) const { return lds8(ring_s + ((uint32_t)p & (kInRing - 1))); }
 
     // issue ring fills ahead of ip as far as the copier's needs allow
@@ -200,149 +142,6 @@ struct Parser {
         ready_end = issued_end;
     }
 };
-
-// Parse one block; pushes descriptors; returns the value to report (bytes produced, or < 0).
-// Positions ip* are in ring space (payload index + skew).
-//
-// Two paths.  WINDOW: lane l decodes the 32 bytes from ip on as if a token started at ip + l (token, offset,
-// one optional length byte), then the true token chain is followed through the window with one shuffle
-// per sequence; the lanes on the chain write their descriptors side by side.  Only sequences without a
-// literal-length extension, with at most one match-length byte and a short match qualify, and only away
-// from the end of the block, where none of the end-of-block rules can fire.  SERIAL: everything else,
-// one sequence at a time with the complete rule set of the safe decoder.
-__device__ int parse_block(Parser& P, int skew, int src_len, int cap, uint32_t dict_len)
-{
-    const uint32_t lane = lane_id();
-    const bool check_offset = dict_len < 65536u;                       // cbits/lz4.c:1764
-    const int iend = skew + src_len;                                   // ring-space end of the payload
-    const uint32_t ring_s = P.ring_s;
-    int ip = skew, op = 0;
-    P.end = iend;
-    P.issued_end = P.ready_end = skew & ~(kFill - 1);
-    P.cur_start = ip;
-    if (cap == 0) {                                                    // :1781-1785
-        if (src_len != 1) return -1;
-        P.ensure(ip, ip + 1);
-        return P.at(ip) == 0 ? 0 : -1;
-    }
-    if (src_len == 0) return -1;                                       // :1787
-    for (;;) {
-        if (P.fill + kWindowSeqs > kQDepth) P.publish(0, 0, ip);
-        if (P.issued_end - ip < 1024) P.top_up(ip);
-        if (ip + 64 > P.ready_end) P.ensure(ip, ip + 64);
-        if (ip + 56 <= iend && op + 1024 <= cap) {
-            // ---- window path
-            const int p = ip + (int)lane;
-            const uint32_t tok = lds8(ring_s + ((uint32_t)p & (kInRing - 1)));
-            const uint32_t lit = tok >> 4, ml = tok & 15u;
-            const uint32_t o = (uint32_t)p + 1u + lit;                 // offset field, if lit < 15
-            const uint32_t b0 = lds8(ring_s + (o & (kInRing - 1)));
-            const uint32_t b1 = lds8(ring_s + ((o + 1) & (kInRing - 1)));
-            const uint32_t b2 = lds8(ring_s + ((o + 2) & (kInRing - 1)));
-            const uint32_t dist = b0 | (b1 << 8);                      // :2055
-            const bool ext = ml == 15u;
-            const uint32_t mlen = ext ? 19u + b2 : ml + 4u;            // one length byte b2 != 255, :2062-2067
-            const uint32_t nxt = lane + 3u + lit + (ext ? 1u : 0u);    // next token, relative to ip
-            const bool simple = lit < 15u && !(ext && b2 == 255u) && mlen <= kShortMatch;
-            const uint32_t packed = nxt | ((lit + mlen) << 8) | (simple ? 0u : 0x80000000u);
-            uint32_t cur = 0, real = 0;
-            int opr = op, my_op = 0;
-            for (;;) {
-                const uint32_t info = __shfl_sync(kFull, packed, cur);
-                if ((int)info < 0) break;
-                if (lane == cur) my_op = opr;
-                real |= 1u << cur;
-                opr += (int)((info >> 8) & 0xFFFFu);
-                cur = info & 0xFFu;
-                if (cur >= 32u) break;
-            }
-            if (real) {
-                const bool mine = (real >> lane) & 1u;
-                // rules that can fire here: offset beyond the dictionary start (:2073), zero offset
-                const bool bad = mine && (dist == 0u || (check_offset && (uint32_t)my_op + lit + dict_len < dist));
-                if (__ballot_sync(kFull, bad)) return -1;
-                const uint32_t rank = __popc(real & lanemask_lt());
-                if (mine) sts128(P.slot_s + 16u * rank, (uint32_t)p + 1u, lit | (mlen << 8) | (dist << 16), (uint32_t)my_op, 0u);
-                const int n = __popc(real);
-                P.slot_s += 16u * (uint32_t)n; P.fill += n;
-                op = opr; ip += (int)cur;
-                continue;
-            }
-        }
-        // ---- serial path: one sequence
-        const uint32_t token = P.at(ip); ip++;
-        uint32_t len = token >> 4;
-        if (len == 15) {                                               // :1977-1983 with reader :1707-1729
-            const int lim = iend - 15;
-            if (ip >= lim) return -1;                                  // initial_error
-            for (;;) {
-                P.ensure(ip, ip + 32);
-                const int p = ip + (int)lane;
-                const uint32_t s = (p < lim) ? P.at(p) : 0u;
-                const bool stop = (p >= lim - 1) || (s != 255u);       // reading position lim-1 ends the run (loop_error keeps the sum)
-                const uint32_t sb = __ballot_sync(kFull, stop);
-                if (sb) {
-                    const int t = __ffs(sb) - 1;
-                    len += 255u * (uint32_t)t + __shfl_sync(kFull, s, t);
-                    ip += t + 1;
-                    break;
-                }
-                len += 255u * 32u; ip += 32;
-            }
-            if (len > 0x7FFFFFFFu) return -1;                          // cannot be a valid run; keeps the int arithmetic below exact
-        }
-        // end rule, :1991-2047
-        const bool last = ((long long)op + len > (long long)cap - kMfLimit) || ((long long)ip + len > (long long)iend - (2 + 1 + kLastLiterals));
-        if (last && ((long long)ip + len != (long long)iend || (long long)op + len > (long long)cap)) return -1;
-        const bool bulk_lit = len > kShortLit;
-        if (last) {
-            if (len) {
-                if (bulk_lit) { if (P.fill) P.publish(0, 0, ip); P.push((uint32_t)ip, len, 0u, 0u); P.publish(kBulk, 0, ip + (int)len); }
-                else { P.ensure(ip, ip + (int)len); P.push((uint32_t)ip, len, (uint32_t)op, 0u); }
-            }
-            return op + (int)len;
-        }
-        const int lit_src = ip;
-        ip += (int)len;
-        P.ensure(ip, ip + 34);
-        const uint32_t dist = P.at(ip) | (P.at(ip + 1) << 8); ip += 2;  // :2055
-        uint32_t mlen = token & 15;
-        if (mlen == 15) {                                              // :2062-2067
-            const int lim = iend - kLastLiterals + 1;
-            for (;;) {
-                P.ensure(ip, ip + 32);
-                const int p = ip + (int)lane;
-                const uint32_t s = (p < iend) ? P.at(p) : 0u;
-                const bool stop = (p >= iend) || (s != 255u);
-                const uint32_t sb = __ballot_sync(kFull, stop);
-                if (sb) {
-                    const int t = __ffs(sb) - 1;
-                    if (ip + t + 1 >= lim) return -1;                  // loop_error
-                    mlen += 255u * (uint32_t)t + __shfl_sync(kFull, s, t);
-                    ip += t + 1;
-                    break;
-                }
-                if (ip + 32 >= lim) return -1;
-                mlen += 255u * 32u; ip += 32;
-            }
-        }
-        mlen += kMinMatch;
-        const int op_seq = op;
-        op += (int)len;
-        const int from = op - (int)dist;
-        if (check_offset && (long long)from + (long long)dict_len < 0) return -1;        // :2073
-        if ((long long)op + mlen > (long long)cap - kLastLiterals) return -1;             // :2076-2078, :2139
-        if (dist == 0) return -1;          // format violation (the reference copies garbage here, :2122-2130)
-        if (bulk_lit || mlen > kShortMatch) {
-            if (P.fill) P.publish(0, 0, lit_src);
-            P.push((uint32_t)lit_src, len, mlen, dist);
-            P.publish(kBulk, 0, ip);
-        } else {
-            P.push((uint32_t)lit_src, len | (mlen << 8) | (dist << 16), (uint32_t)op_seq, 0u);
-        }
-        op += (int)mlen;
-    }
-}
 
 __device__ void parser_main(const DecompressArgs& a, DQueue* q, uint32_t ring_s)
 {
@@ -384,37 +183,6 @@ __device__ void parser_main(const DecompressArgs& a, DQueue* q, uint32_t ring_s)
 }
 
 // ------------------------------------------------------------------ copier ----
-
-// coherent (not read-only-path) cooperative copy, non-overlapping, arbitrary alignment
-__device__ __forceinline__ void warp_copy_rw(uint8_t* dst, const uint8_t* src, uint32_t len)
-{
-    const uint32_t lane = lane_id();
-    if (len < 96) {
-        for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
-        return;
-    }
-    uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
-    if (lane < head) dst[lane] = src[lane];
-    dst += head; src += head; len -= head;
-    const uint32_t nvec = len >> 4;
-    uintptr_t sa = reinterpret_cast<uintptr_t>(src);
-    const uint32_t sh = (uint32_t)(sa & 3) * 8;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
-    uint4* dv = reinterpret_cast<uint4*>(dst);
-    if ((sa & 15) == 0) {
-        const uint4* sv = reinterpret_cast<const uint4*>(src);
-        for (uint32_t v = lane; v < nvec; v += 32) dv[v] = sv[v];
-    } else {
-        for (uint32_t v = lane; v < nvec; v += 32) {
-            const uint32_t* qd = sw + 4 * v;
-            uint32_t x0 = qd[0], x1 = qd[1], x2 = qd[2], x3 = qd[3], x4 = sh ? qd[4] : 0u;
-            dv[v] = make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh),
-                               __funnelshift_r(x2, x3, sh), __funnelshift_r(x3, x4, sh));
-        }
-    }
-    const uint32_t done = nvec << 4, tail = len - done;
-    if (lane < tail) dst[done + lane] = src[done + lane];
-}
 
 struct Copier {
     uint32_t in_s, out_s;       // shared addresses of the rings
@@ -684,21 +452,35 @@ decompress_kernel(DecompressArgs a)
 
 }  // namespace
 
+// SM count per device, looked up once (thread-safe: several host threads launch on different devices)
+cudaError_t device_sm_count(int* out)
+{
+    static std::mutex mu;
+    static int sm_counts[64] = {0};
+    int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!sm_counts[dev]) { e = cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e; }
+    *out = sm_counts[dev];
+    return cudaSuccess;
+}
+
 cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream)
 {
-    static int sm_counts[64] = {0};     // per device
-    int dev = 0; cudaError_t e0 = cudaGetDevice(&dev); if (e0 != cudaSuccess) return e0;
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (!sm_counts[dev]) {
-        e0 = cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev); if (e0 != cudaSuccess) return e0;
-    }
-    const int sm_count = sm_counts[dev];
+    int sm_count = 0;
+    cudaError_t e0 = device_sm_count(&sm_count); if (e0 != cudaSuccess) return e0;
     if (a.n_streams <= 0) return cudaSuccess;
-    const int max_ctas = sm_count * 16;
-    const int grid = a.n_streams < max_ctas ? a.n_streams : max_ctas;
     static const char* dbg = getenv("B200LZ4_DECODE_DEBUG");
+    static const char* wide_env = getenv("B200LZ4_DWIDE");           // A/B switch: "0" never, "1" whenever the arena allows
     DecompressArgs b = a;
     b.debug = dbg ? atoi(dbg) : 0;
+    // Wide kernel (one stream per SM, parallel block parsers + out-of-order copiers): linked streams when there are
+    // few enough of them that the narrow kernel would leave most of the GPU idle; few independent blocks likewise.
+    bool wide = a.stream_first ? (a.n_streams <= 4 * sm_count) : (a.n_streams <= sm_count);
+    if (wide_env) wide = wide_env[0] == '1';
+    if (wide && a.wide_arena) return launch_decompress_wide(b, sm_count, stream);
+    const int max_ctas = sm_count * 16;
+    const int grid = a.n_streams < max_ctas ? a.n_streams : max_ctas;
     decompress_kernel<<<grid, 64, 0, stream>>>(b);
     return cudaGetLastError();
 }

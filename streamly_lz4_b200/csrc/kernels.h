@@ -23,7 +23,18 @@ struct DecompressArgs {
     int header; int max_block;
     Scratch* scratch;
     int debug;                  // measurement switches (B200LZ4_DECODE_DEBUG): 1 = copier skips every copy (parser-bound rate)
+    uint4* wide_arena;          // descriptor rings of the wide kernel: wide_ctas x kWideArenaPerCta bytes (NULL: narrow kernel only)
+    int wide_ctas;
 };
+
+// decompress_kernel_wide keeps its parsed-ahead sequence descriptors in global memory (L2): per CTA, kWideParsers rings of
+// kWideRingBatches batches of 32 descriptors of 16 bytes.
+constexpr int kWideParsers = 8;
+constexpr int kWideRingBatches = 256;
+constexpr size_t kWideArenaPerCta = size_t(kWideParsers) * kWideRingBatches * 32 * 16;     // 1 MiB
+constexpr int kWideMaxCtas = 160;
+// layout of the scratch block the *_dev entry points take: [Scratch counters][wide arena]
+constexpr size_t kScratchBytes = sizeof(Scratch) + kWideMaxCtas * kWideArenaPerCta;
 
 struct CompactArgs {
     const uint8_t* slots; const int64_t* slot_off; const int32_t* len; int n_blocks;
@@ -35,6 +46,8 @@ struct CompactArgs {
 
 cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream);
 cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream);
+cudaError_t launch_decompress_wide(const DecompressArgs& a, int sm_count, cudaStream_t stream);
+cudaError_t device_sm_count(int* out);
 cudaError_t launch_compact(const CompactArgs& a, cudaStream_t stream);
 cudaError_t launch_reframe(const uint8_t* buf, int64_t len, int header, int has_end_mark,
                            int64_t* block_off, int32_t* block_len, int64_t max_blocks, int64_t* result, cudaStream_t stream);

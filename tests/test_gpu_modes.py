@@ -14,6 +14,24 @@ SUBSET = ["tests/test_gpu_fuzz.py", "tests/test_gpu_parity.py", "-k",
           "random_round_trips or echoing or split_over or generators or edge_sizes or acceleration_sweep or linked_state"]
 
 
+DECODE_SUBSET = ["tests/test_gpu_fuzz.py", "tests/test_gpu_parity.py", "-k",
+                 "handbuilt or corrupted or random_round_trips or echoing or split_over or generators or edge_sizes or "
+                 "empty_and_tiny or block_max or large_blocks or linked_state or malformed or fragmented"]
+
+
+@pytest.mark.parametrize("env", [{"B200LZ4_DWIDE": "0"},        # every decode through the narrow kernel (parser + copier warp per stream)
+                                 {"B200LZ4_DWIDE": "1"}],       # every decode through the wide kernel (8 parsers + 7 copiers per stream)
+                         ids=["narrow", "wide"])
+def test_decoder_parity_with_forced_kernel(ctx, env):
+    """The decoder has two kernels chosen by the number of streams in a launch; both must make the reference's
+    accept/reject decisions and produce its bytes on every fuzz and edge case."""
+    e = dict(os.environ, **env)
+    out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", *DECODE_SUBSET], cwd=ROOT, env=e,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert " passed" in out.stdout
+
+
 @pytest.mark.parametrize("env", [{"B200LZ4_NO_WIDE": "1", "B200LZ4_COMPACT": "1"},      # everything through the compact-table kernel
                                  {"B200LZ4_NO_WIDE": "1", "B200LZ4_COMPACT": "0"}],     # everything through the classic dense kernel
                          ids=["compact", "classic"])
