@@ -11,14 +11,16 @@
 //                    the parser reports how far before its block a match reaches, the dispatcher compares).  Each
 //                    parser writes 32-descriptor batches into its own ring in GLOBAL memory (256 batches, a whole
 //                    64 KiB block: L2-resident) and a 16-byte batch header into a shared-memory ring.
-//   7 COPIER warps   take batches strictly in stream order from a dispatcher (a critical section: which parser's ring
-//                    is next, the batch's absolute output position, flow control) but EXECUTE them out of order.  The
+//   1 DISPATCHER warp hands batches out strictly in stream order as numbered tickets (which parser's ring is next, the
+//                    batch's absolute output position, flow control, in-order retirement, stream begin / end).
+//   7 COPIER warps   draw tickets and EXECUTE them out of order.  The
 //                    stream's last 128 KiB of output live in a shared-memory ring indexed by stream position, with one
 //                    READY bit per byte (lap parity, so bits never need clearing): literals are copied at once, a
 //                    match waits (spinning on the bits) only for the bytes it really reads, then publishes its own.
-//                    Matches that are ready together are copied lane-parallel; a dependency chain inside a batch
-//                    (records, runs) degrades to one warp-cooperative copy per link, as in the narrow kernel.  Every
-//                    warp flushes its own batch to global memory with 128-bit stores.
+//                    Matches whose source lies before the batch are copied lane-parallel as they become ready; matches
+//                    that read the batch's own output (records, runs: a dependency chain) then run in order, one
+//                    warp-cooperative copy per link, exactly like the narrow kernel's phase B.  Every warp flushes its
+//                    own batch to global memory with 128-bit stores.
 //
 // Flow control: a batch may only be handed out while its end is less than 60 KiB ahead of the in-order completion
 // frontier (the ring holds 128 KiB, matches reach 64 KiB back); long sequences are cut into pieces of 16 KiB by the
@@ -35,7 +37,7 @@ namespace {
 
 constexpr int kWP = kWideParsers;                 // parser warps
 constexpr int kWC = 7;                            // copier warps
-constexpr int kWThreads = (kWP + kWC) * 32;
+constexpr int kWThreads = (kWP + 1 + kWC) * 32;   // + the dispatcher warp
 constexpr uint32_t kWOut = 131072, kWM = kWOut - 1;      // output ring (bytes), indexed by stream position
 constexpr int kWBitWords = kWOut / 32;            // one ready bit per ring byte
 constexpr int kWR = kWideRingBatches;             // batches per parser ring
@@ -45,19 +47,19 @@ constexpr int kRunAhead = 61440;                  // a batch may end at most thi
 constexpr uint32_t kPiece = 16384;                // long sequences are cut into pieces of this many output bytes
 constexpr uint32_t kSeedBase = 65536;             // stream position of the first output byte after (re)seeding
 
-struct WCtl {                                     // dispatcher state (shared memory; guarded by `lock` unless noted)
-    uint32_t lock, finished, stream_open, reseed_pending, persist_pending, next_iter;
-    int s, b0, b1, cur_b;
-    uint32_t base;                                // stream position of the current block's first output byte
-    uint32_t dict_len;                            // length of the last successful block (cbits/lz4.c:2353-2355)
-    uint32_t valid_lo;                            // lowest stream position a match may read
-    uint32_t T, F, fpos;                          // tickets handed out / completed in order; position below which all output is final
-    const uint8_t* last_out; int last_len; int pad_;
-    uint32_t rd[kWP];                             // next batch of each parser ring to hand out
-    uint32_t wr_pub[kWP];                         // batches published (written by the parser, lock-free)
-    uint32_t cons[kWP];                           // batches retired (read by the parser, lock-free)
-    uint32_t done[kTickets];                      // ticket t complete <=> done[t % 64] == t + 1 (written by copiers, lock-free)
-    uint32_t tend[kTickets], tn[kTickets], tj[kTickets];
+struct WTicket { uint32_t jn, cf, op_start, base, valid_lo; int blk; uint32_t pad_[2]; };   // 32 bytes; jn = parser << 16 | ring slot
+
+struct WCtl {                                     // shared memory
+    uint32_t next_ticket;                         // copiers draw tickets here (atomicAdd)
+    uint32_t finished;                            // dispatcher: no more tickets will be issued
+    uint32_t pad_[2];
+    uint32_t rd[kWP];                             // dispatcher: next batch of each parser ring to hand out
+    uint32_t wr_pub[kWP];                         // parsers: batches published
+    uint32_t cons[kWP];                           // dispatcher: batches retired (parsers wait on it for ring space)
+    uint32_t tready[kTickets];                    // dispatcher: ticket t issued <=> tready[t % 64] == t + 1
+    uint32_t done[kTickets];                      // copiers: ticket t complete <=> done[t % 64] == t + 1
+    uint32_t tend[kTickets], tn[kTickets], tj[kTickets];      // dispatcher-private: end position / ring slot / parser of a ticket
+    WTicket ticket[kTickets];
 };
 
 __device__ __forceinline__ uint32_t vld(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
@@ -132,7 +134,8 @@ __device__ __forceinline__ bool bits_ready_coop(uint32_t bits_s, uint32_t pos, u
 // ------------------------------------------------------------- ring <-> global ----
 __device__ __forceinline__ uint32_t rix(uint32_t out_s, uint32_t pos) { return out_s + (pos & kWM); }
 
-// n bytes of global memory -> ring positions [pos, pos + n); all lanes, identical arguments
+// n bytes of global memory -> ring positions [pos, pos + n); all lanes, identical arguments.  Four loads in flight
+// per lane (a serial chain of this warp: latency, not bandwidth, is what it pays for).
 template <bool kReadOnly>
 __device__ __forceinline__ void copy_g2r(uint32_t out_s, uint32_t pos, const uint8_t* src, uint32_t n)
 {
@@ -142,8 +145,14 @@ __device__ __forceinline__ void copy_g2r(uint32_t out_s, uint32_t pos, const uin
     if (lane < head) sts8(rix(out_s, pos + lane), kReadOnly ? (uint32_t)__ldg(src + lane) : (uint32_t)src[lane]);
     pos += head; src += head; n -= head;
     const uint32_t nw = n >> 2;
-    for (uint32_t w = lane; w < nw; w += 32)
-        sts32(rix(out_s, pos + 4u * w), kReadOnly ? ldg_u32_unaligned(src + 4u * w) : ld_u32_unaligned(src + 4u * w));
+    auto ld = [&](uint32_t w) { return kReadOnly ? ldg_u32_unaligned(src + 4u * w) : ld_u32_unaligned(src + 4u * w); };
+    uint32_t w = lane;
+    for (; w + 96u < nw; w += 128u) {
+        const uint32_t a = ld(w), b = ld(w + 32u), c = ld(w + 64u), d = ld(w + 96u);
+        sts32(rix(out_s, pos + 4u * w), a); sts32(rix(out_s, pos + 4u * (w + 32u)), b);
+        sts32(rix(out_s, pos + 4u * (w + 64u)), c); sts32(rix(out_s, pos + 4u * (w + 96u)), d);
+    }
+    for (; w < nw; w += 32u) sts32(rix(out_s, pos + 4u * w), ld(w));
     const uint32_t done = nw << 2, tail = n - done;
     if (lane < tail) sts8(rix(out_s, pos + done + lane), kReadOnly ? (uint32_t)__ldg(src + done + lane) : (uint32_t)src[done + lane]);
 }
@@ -159,7 +168,12 @@ __device__ __forceinline__ void flush_r2g(uint32_t out_s, uint8_t* gdst, uint32_
     const uint32_t nvec = n >> 4;
     uint4* gv = reinterpret_cast<uint4*>(gdst);
     if ((pos & 15u) == 0) {
-        for (uint32_t v = lane; v < nvec; v += 32) gv[v] = lds128(rix(out_s, pos + 16u * v));
+        uint32_t v = lane;
+        for (; v + 32u < nvec; v += 64u) {
+            const uint4 a = lds128(rix(out_s, pos + 16u * v)), b = lds128(rix(out_s, pos + 16u * (v + 32u)));
+            gv[v] = a; gv[v + 32u] = b;
+        }
+        for (; v < nvec; v += 32u) gv[v] = lds128(rix(out_s, pos + 16u * v));
     } else {
         const uint32_t sh = (pos & 3u) * 8u;
         for (uint32_t v = lane; v < nvec; v += 32) {
@@ -187,16 +201,23 @@ __device__ __forceinline__ void coop_short_match(uint32_t out_s, uint32_t dst, u
 }
 
 // A long match piece inside the ring, all lanes: rounds of one period each (the period's source is complete before
-// the round starts); periods below 32 are replicated from registers.
+// the round starts; several periods per round once they have been written); periods below 32 are replicated from
+// registers.
 __device__ __forceinline__ void coop_long_match(uint32_t out_s, uint32_t dst, uint32_t len, uint32_t dist)
 {
     const uint32_t lane = lane_id();
     const uint32_t src = dst - dist;
     if (dist >= 32u) {
-        for (uint32_t done = 0; done < len; done += dist) {
-            const uint32_t n = min(dist, len - done);
-            for (uint32_t i = lane; i < n; i += 32) sts8(rix(out_s, dst + done + i), lds8(rix(out_s, src + done + i)));
+        const uint32_t kmax = dist < 4096u ? 4096u / dist : 1u;
+        uint32_t done = 0;                              // bytes [0, done) written
+        while (done < len) {
+            uint32_t k = (done + dist) / dist;          // whole periods available below dst + done: any multiple of dist is a valid offset
+            if (k > kmax) k = kmax;
+            const uint32_t P = k * dist;
+            const uint32_t n = min(P, len - done);
+            for (uint32_t i = lane; i < n; i += 32) sts8(rix(out_s, dst + done + i), lds8(rix(out_s, dst + done + i - P)));
             __syncwarp();
+            done += n;
         }
     } else {
         const uint32_t pat = lds8(rix(out_s, src + (lane < dist ? lane : 0u)));
@@ -338,140 +359,141 @@ __device__ void wparser_main(const DecompressArgs& a, int j, WCtl* ctl, uint32_t
 }
 
 // ------------------------------------------------------------------ dispatcher ----
-__device__ __forceinline__ void wlock(WCtl* c)
-{
-    if (lane_id() == 0) while (atomicCAS(&c->lock, 0u, 1u) != 0u) __nanosleep(64);
-    __syncwarp();
-    __threadfence_block();
-}
-__device__ __forceinline__ void wunlock(WCtl* c)
-{
-    __threadfence_block();
-    __syncwarp();
-    if (lane_id() == 0) atomicExch(&c->lock, 0u);
-}
-// advance the in-order completion frontier over finished tickets; retire their ring slots (lock held; every lane runs
-// the same code on the same shared-memory words)
-__device__ __forceinline__ void wadvance(WCtl* c)
-{
-    uint32_t F = vld(&c->F);
-    const uint32_t T = vld(&c->T);
-    while (F != T && vld(&c->done[F & (kTickets - 1)]) == F + 1) {
-        const uint32_t k = F & (kTickets - 1);
-        vst(&c->fpos, vld(&c->tend[k]));
-        vst(&c->cons[vld(&c->tj[k])], vld(&c->tn[k]) + 1);
-        F++;
-    }
-    vst(&c->F, F);
-}
-__device__ __forceinline__ void wdrain(WCtl* c)
-{
-    for (;;) { wadvance(c); if (vld(&c->F) == vld(&c->T)) break; __nanosleep(100); }
-    __threadfence_block();
-}
+// One warp; every lane runs the same scalar code on the same shared-memory words (loads broadcast, stores coincide), the
+// cooperative parts (seeding the ring, keeping the stream tail) use all lanes.
+struct WDispatch {
+    WCtl* c;
+    uint32_t T, F, fpos;        // tickets issued / retired in order; stream position below which all output is final
 
-__device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, uint32_t bits_s, uint32_t hdrs_s,
-                             uint32_t stage_s, const uint4* garena)
+    // retire finished tickets in order; free their ring slots for the parsers
+    __device__ __forceinline__ void advance()
+    {
+        while (F != T && vld(&c->done[F & (kTickets - 1)]) == F + 1) {
+            const uint32_t k = F & (kTickets - 1);
+            fpos = vld(&c->tend[k]);
+            vst(&c->cons[vld(&c->tj[k])], vld(&c->tn[k]) + 1);
+            F++;
+        }
+    }
+    __device__ __forceinline__ void drain()
+    {
+        for (;;) { advance(); if (F == T) break; __nanosleep(100); }
+        __threadfence_block();
+    }
+};
+
+__device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, uint32_t bits_s, uint32_t hdrs_s)
 {
     const uint32_t lane = lane_id();
-    volatile WCtl* const c = ctl;        // every field access below is a real shared-memory access
+    WDispatch D{ctl, 0u, 0u, kSeedBase};
+    for (int s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
+        const int b0 = a.stream_first ? a.stream_first[s] : a.first_block + s;
+        const int b1 = a.stream_first ? a.stream_first[s + 1] : b0 + 1;
+        DState* st = a.states ? reinterpret_cast<DState*>(a.states[s]) : nullptr;
+        // ---- open the stream: the ring restarts at kSeedBase with the kept tail of the previous call as dictionary
+        D.drain();
+        uint32_t dict_len = 0, kept = 0;
+        if (st && st->prev_len) { dict_len = st->prev_len; kept = st->kept; wseed(out_s, bits_s, st->tail + 65536 - kept, kept); }
+        else wseed(out_s, bits_s, nullptr, 0u);
+        uint32_t base = kSeedBase, valid_lo = kSeedBase - kept;
+        D.fpos = kSeedBase;
+        const uint8_t* last_out = nullptr; int last_len = 0;
+        for (int blk = b0; blk < b1; blk++) {
+            const uint32_t j = (uint32_t)(blk - b0) % (uint32_t)kWP;
+            for (;;) {                                                      // the batches of this block, in order
+                const uint32_t n = vld(&ctl->rd[j]);
+                while (vld(&ctl->wr_pub[j]) == n) { D.advance(); __nanosleep(20); }    // (retiring slots may be what a parser waits for)
+                __threadfence_block();
+                const uint4 h = lds128(hdrs_s + (j * kWR + (n & (kWR - 1))) * 16u);
+                const uint32_t e = base + h.z;
+                // flow control: the ring holds 128 KiB and matches reach 64 KiB back, so nothing may be written more than
+                // 60 KiB beyond the completion frontier; ticket slots are reused after 64
+                for (;;) {
+                    D.advance();
+                    if ((int)(e - D.fpos) <= kRunAhead && D.T - D.F < (uint32_t)(kTickets - 16)) break;
+                    __nanosleep(20);
+                }
+                const uint32_t k = D.T & (kTickets - 1);
+                vst(&ctl->tend[k], e); vst(&ctl->tj[k], j); vst(&ctl->tn[k], n);
+                if (lane == 0) {
+                    WTicket* tk = &ctl->ticket[k];
+                    tk->jn = (j << 16) | (n & (kWR - 1)); tk->cf = h.x; tk->op_start = h.y; tk->base = base; tk->valid_lo = valid_lo; tk->blk = blk;
+                    __threadfence_block();
+                    vst(&ctl->tready[k], D.T + 1);
+                }
+                __syncwarp();
+                D.T++;
+                vst(&ctl->rd[j], n + 1);
+                if ((int)h.x & kEndBlock) {
+                    int r = ((int)h.x & kFailed) ? -1 : (int)h.z;
+                    if (r >= 0 && dict_len < 65536u && h.w > dict_len) r = -1;      // cbits/lz4.c:2073, deferred: a match reached below the dictionary
+                    if (lane == 0) a.out_len[blk] = r;
+                    if (r > 0) {                                            // cbits/lz4.c:2353-2355: this output is the next dictionary
+                        base += (uint32_t)r; dict_len = (uint32_t)r;
+                        valid_lo = base - ((uint32_t)r < 65536u ? (uint32_t)r : 65536u);
+                        last_out = a.dst + a.dst_off[blk]; last_len = r;
+                    } else if (r < 0 && blk + 1 < b1) {
+                        // what the failed block wrote into the ring is garbage: restart the ring from the last good output
+                        // (which stays the dictionary), taken from global memory
+                        D.drain();
+                        kept = 0; dict_len = 0;
+                        if (last_out) {
+                            dict_len = (uint32_t)last_len; kept = dict_len < 65536u ? dict_len : 65536u;
+                            wseed(out_s, bits_s, last_out + last_len - kept, kept);
+                        } else if (st && st->prev_len) {
+                            dict_len = st->prev_len; kept = st->kept;
+                            wseed(out_s, bits_s, st->tail + 65536 - kept, kept);
+                        } else wseed(out_s, bits_s, nullptr, 0u);
+                        base = kSeedBase; valid_lo = kSeedBase - kept; D.fpos = kSeedBase;
+                    }
+                    break;
+                }
+            }
+        }
+        // ---- close the stream: keep the reachable tail of the last output for the next call
+        if (st && last_out) {
+            D.drain();
+            const uint32_t kp = last_len < 65536 ? (uint32_t)last_len : 65536u;
+            warp_copy_rw(st->tail + 65536 - kp, last_out + last_len - kp, kp);
+            __syncwarp();
+            if (lane == 0) { st->prev_len = (uint32_t)last_len; st->kept = kp; }
+        }
+    }
+    D.drain();
+    vst(&ctl->finished, 1u);
+}
+
+// ---------------------------------------------------------------------- copiers ----
+__device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, uint32_t bits_s, uint32_t stage_s, const uint4* garena)
+{
+    constexpr uint32_t M = kWM;
+    const uint32_t lane = lane_id();
     int cached_blk = -1; uint8_t* blk_out = nullptr; const uint8_t* blk_gbase = nullptr;
     for (;;) {
-        wlock(ctl);
-        // ---- stream bookkeeping: close / reseed / open
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&ctl->next_ticket, 1u);
+        t = __shfl_sync(kFull, t, 0);
+        const uint32_t k = t & (kTickets - 1);
         bool fin = false;
-        for (;;) {
-            if (c->finished) { fin = true; break; }
-            DState* st = (a.states && c->s >= 0) ? reinterpret_cast<DState*>(a.states[c->s]) : nullptr;
-            if (c->reseed_pending) {
-                // a block of this stream failed: what it wrote into the ring is garbage; restart the ring from the last
-                // good output (which stays the dictionary, cbits/lz4.c:2353), taken from global memory
-                wdrain(ctl);
-                uint32_t kept = 0, dl = 0;
-                if (c->last_out) {
-                    dl = (uint32_t)c->last_len; kept = dl < 65536u ? dl : 65536u;
-                    wseed(out_s, bits_s, c->last_out + c->last_len - kept, kept);
-                } else if (st && st->prev_len) {
-                    dl = st->prev_len; kept = st->kept;
-                    wseed(out_s, bits_s, st->tail + 65536 - kept, kept);
-                } else wseed(out_s, bits_s, nullptr, 0u);
-                c->base = kSeedBase; c->fpos = kSeedBase; c->dict_len = dl; c->valid_lo = kSeedBase - kept;
-                c->reseed_pending = 0u;
-            }
-            if (c->stream_open) break;
-            wdrain(ctl);
-            if (c->persist_pending) {        // keep the reachable tail of the last output for the next call
-                const uint32_t kept = c->last_len < 65536 ? (uint32_t)c->last_len : 65536u;
-                warp_copy_rw(st->tail + 65536 - kept, c->last_out + c->last_len - kept, kept);
-                __syncwarp();
-                if (lane == 0) { st->prev_len = (uint32_t)c->last_len; st->kept = kept; }
-                c->persist_pending = 0u;
-            }
-            const int s = (int)blockIdx.x + (int)c->next_iter * (int)gridDim.x;
-            if (s >= a.n_streams) { c->finished = 1u; fin = true; break; }
-            c->next_iter = c->next_iter + 1;
-            const int b0 = a.stream_first ? a.stream_first[s] : a.first_block + s;
-            const int b1 = a.stream_first ? a.stream_first[s + 1] : b0 + 1;
-            const DState* ns = a.states ? reinterpret_cast<const DState*>(a.states[s]) : nullptr;
-            uint32_t kept = 0, dl = 0;
-            if (ns && ns->prev_len) { dl = ns->prev_len; kept = ns->kept; wseed(out_s, bits_s, ns->tail + 65536 - kept, kept); }
-            else wseed(out_s, bits_s, nullptr, 0u);
-            c->s = s; c->b0 = b0; c->b1 = b1; c->cur_b = b0;
-            c->last_out = nullptr; c->last_len = 0;
-            c->base = kSeedBase; c->fpos = kSeedBase; c->dict_len = dl; c->valid_lo = kSeedBase - kept;
-            c->stream_open = b0 < b1 ? 1u : 0u;
-            __syncwarp();
-        }
-        if (fin) { wunlock(ctl); break; }
-
-        // ---- hand out the next batch of the stream (this warp takes it)
-        const int blk = c->cur_b;
-        const uint32_t j = (uint32_t)(blk - c->b0) % (uint32_t)kWP;
-        const uint32_t n = c->rd[j];
-        while (c->wr_pub[j] == n) { wadvance(ctl); __nanosleep(40); }      // (retiring slots may be what the parser waits for)
+        while (vld(&ctl->tready[k]) != t + 1) { if (vld(&ctl->finished)) { fin = true; break; } __nanosleep(20); }
+        if (fin) break;
         __threadfence_block();
-        const uint4 h = lds128(hdrs_s + (j * kWR + (n & (kWR - 1))) * 16u);
-        const uint32_t base = c->base, valid_lo = c->valid_lo;
-        const uint32_t e = base + h.z;
-        for (;;) {
-            wadvance(ctl);
-            if ((int)(e - c->fpos) <= kRunAhead && c->T - c->F < (uint32_t)(kTickets - 8)) break;
-            __nanosleep(40);
-        }
-        const uint32_t t = c->T;
-        {
-            const uint32_t k = t & (kTickets - 1);
-            c->tend[k] = e; c->tj[k] = j; c->tn[k] = n;
-            c->T = t + 1; c->rd[j] = n + 1;
-        }
-        const int cf = (int)h.x;
-        const uint32_t op_start = h.y;
-        if (cf & kEndBlock) {
-            int r = (cf & kFailed) ? -1 : (int)h.z;
-            const uint32_t dl = c->dict_len;
-            if (r >= 0 && dl < 65536u && h.w > dl) r = -1;                  // cbits/lz4.c:2073, deferred: a match reached below the dictionary
-            if (lane == 0) a.out_len[blk] = r;
-            if (r > 0) {                                                    // cbits/lz4.c:2353-2355
-                c->base = base + (uint32_t)r; c->dict_len = (uint32_t)r;
-                c->valid_lo = base + (uint32_t)r - ((uint32_t)r < 65536u ? (uint32_t)r : 65536u);
-                c->last_out = a.dst + a.dst_off[blk]; c->last_len = r;
-            } else if (r < 0 && blk + 1 < c->b1) c->reseed_pending = 1u;
-            c->cur_b = blk + 1;
-            if (blk + 1 == c->b1) { c->stream_open = 0u; c->persist_pending = (a.states && c->last_out) ? 1u : 0u; }
-        }
-        wunlock(ctl);
+        const uint4 tk = lds128(smem_u32(&ctl->ticket[k]));
+        const uint32_t valid_lo = vld(&ctl->ticket[k].valid_lo);
+        const int blk = (int)vld(reinterpret_cast<const uint32_t*>(&ctl->ticket[k].blk));
+        const uint32_t j = tk.x >> 16, slot = tk.x & 0xFFFFu, base = tk.w, op_start = tk.z;
+        const int cf = (int)tk.y;
 
-        // ---- execute it
         const int cnt = cf & kCountMask;
         uint4 d = make_uint4(0, 0, 0, 0);
-        if ((int)lane < cnt) d = ld_cg_128(garena + ((size_t)j * kWR + (n & (kWR - 1))) * 32 + lane);
+        if ((int)lane < cnt) d = ld_cg_128(garena + ((size_t)j * kWR + slot) * 32 + lane);
         if (blk != cached_blk) {
             const BlockGeom g = block_geom(a, blk);
             blk_out = g.out; blk_gbase = g.payload - (reinterpret_cast<uintptr_t>(g.payload) & 15);
             cached_blk = blk;
         }
         if (cf & kBulk) {
-            // one piece of a long sequence
+            // ---- one piece of a long sequence
             const uint32_t lit_src = __shfl_sync(kFull, d.x, 0), lit = __shfl_sync(kFull, d.y, 0);
             const uint32_t mlen = __shfl_sync(kFull, d.z, 0), dist = __shfl_sync(kFull, d.w, 0);
             const uint32_t pos = base + op_start;
@@ -481,13 +503,13 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
                 __threadfence_block();
                 __syncwarp();
                 bits_set_coop(bits_s, pos, lit);
-                warp_copy_ro(gout, blk_gbase + lit_src, lit);
+                flush_r2g(out_s, gout, pos, lit);
             }
             if (mlen) {
                 const uint32_t m_pos = pos + lit, from = m_pos - dist;
                 if ((int)(from - valid_lo) >= 0) {                          // (else: the block is rejected at its end; nothing to wait for)
                     const uint32_t need_n = mlen < dist ? mlen : dist;
-                    while (!bits_ready_coop(bits_s, from, need_n)) __nanosleep(64);
+                    while (!bits_ready_coop(bits_s, from, need_n)) __nanosleep(32);
                     __threadfence_block();
                     coop_long_match(out_s, m_pos, mlen, dist);
                 }
@@ -497,7 +519,7 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
                 flush_r2g(out_s, gout + lit, m_pos, mlen);
             }
         } else if (cnt) {
-            // up to 32 short sequences, one per lane
+            // ---- up to 32 short sequences, one per lane
             const bool is_seq = (int)lane < cnt;
             const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
             const uint32_t lit_pos = base + d.z, m_pos = lit_pos + lit, from = m_pos - dist;
@@ -511,56 +533,83 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
             const bool staged = nvec <= (uint32_t)(kWStage / 16);
             if (staged) {
                 const uint4* gv = reinterpret_cast<const uint4*>(blk_gbase + lo);
-                for (uint32_t v = lane; v < nvec; v += 32) { const uint4 x = ldg_na_u128(gv + v); sts128(stage_s + 16u * v, x.x, x.y, x.z, x.w); }
+                uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, x2 = x0;       // (at most 96 vectors: three per lane, all in flight at once)
+                if (lane < nvec) x0 = ldg_na_u128(gv + lane);
+                if (lane + 32u < nvec) x1 = ldg_na_u128(gv + lane + 32u);
+                if (lane + 64u < nvec) x2 = ldg_na_u128(gv + lane + 64u);
+                if (lane < nvec) sts128(stage_s + 16u * lane, x0.x, x0.y, x0.z, x0.w);
+                if (lane + 32u < nvec) sts128(stage_s + 16u * (lane + 32u), x1.x, x1.y, x1.z, x1.w);
+                if (lane + 64u < nvec) sts128(stage_s + 16u * (lane + 64u), x2.x, x2.y, x2.z, x2.w);
             }
             __syncwarp();
             if (is_seq && lit) {
                 if (staged) {
                     const uint32_t sl = stage_s + (d.x - lo);
-                    for (uint32_t i = 0; i < lit; i++) sts8(rix(out_s, lit_pos + i), lds8(sl + i));
+                    for (uint32_t i = 0; i < lit; i++) sts8(out_s + ((lit_pos + i) & M), lds8(sl + i));
                 } else {
                     const uint8_t* gp = blk_gbase + d.x;
-                    for (uint32_t i = 0; i < lit; i++) sts8(rix(out_s, lit_pos + i), (uint32_t)__ldg(gp + i));
+                    for (uint32_t i = 0; i < lit; i++) sts8(out_s + ((lit_pos + i) & M), (uint32_t)__ldg(gp + i));
                 }
             }
             __threadfence_block();
             if (is_seq && lit) bits_set(bits_s, lit_pos, lit);
-            // matches: whichever are ready, round after round
-            bool pend = is_seq && mlen != 0;
+            const bool has_match = is_seq && mlen != 0;
             const uint32_t need_n = mlen < dist ? mlen : dist;
             const bool doomed = (int)(from - valid_lo) < 0;                 // reads below the dictionary: the block will be rejected
-            for (;;) {
+            // phase X: matches whose source lies wholly before this batch (other warps' output): whichever are ready, lane-parallel
+            const bool external = has_match && (int)(from + need_n - s_pos) <= 0;
+            bool pend = external;
+            while (__ballot_sync(kFull, pend)) {
                 const bool rdy = pend && (doomed || bits_ready(bits_s, from, need_n));
-                const uint32_t rb = __ballot_sync(kFull, rdy);
-                if (rb) {
+                if (__ballot_sync(kFull, rdy)) {
                     __threadfence_block();
-                    if (__popc(rb) <= 4) {                                  // a chain: one warp-wide copy per link
-                        uint32_t todo = rb;
-                        while (todo) {
-                            const int l = __ffs(todo) - 1; todo &= todo - 1;
-                            const uint32_t c_dst = __shfl_sync(kFull, m_pos, l), c_len = __shfl_sync(kFull, mlen, l);
-                            const uint32_t c_dist = __shfl_sync(kFull, dist, l);
-                            const bool c_doomed = __shfl_sync(kFull, (int)doomed, l) != 0;
-                            if (!c_doomed) coop_short_match(out_s, c_dst, c_len, c_dist);
-                        }
-                    } else if (rdy && !doomed) {                            // many at once: every lane copies its own
-                        for (uint32_t i = 0; i < mlen; i++) sts8(rix(out_s, m_pos + i), lds8(rix(out_s, from + i)));
-                    }
+                    if (rdy && !doomed) for (uint32_t i = 0; i < mlen; i++) sts8(out_s + ((m_pos + i) & M), lds8(out_s + ((from + i) & M)));
                     __threadfence_block();
-                    __syncwarp();
                     if (rdy) bits_set(bits_s, m_pos, mlen);
                     pend = pend && !rdy;
+                } else __nanosleep(20);
+            }
+            // phase I: matches that read bytes of this batch, in order, each copied by all lanes (the narrow kernel's phase B).
+            // A source may start up to 64 bytes below the batch: those bytes belong to earlier tickets and must be complete.
+            uint32_t dep = __ballot_sync(kFull, has_match && !external);
+            if (dep) {
+                const int below = (has_match && !external && !doomed) ? (int)(s_pos - from) : 0;      // > 0: reads that many bytes below the batch
+                const int reach = __reduce_max_sync(kFull, below);
+                if (reach > 0) {
+                    while (!bits_ready_coop(bits_s, s_pos - (uint32_t)reach, (uint32_t)reach)) __nanosleep(20);
+                    __threadfence_block();
                 }
-                if (!__ballot_sync(kFull, pend)) break;
-                if (!rb) __nanosleep(32);
+                __syncwarp();
+                const uint32_t par_s = stage_s;                             // (the staged input has been consumed)
+                {
+                    const uint32_t inv = (dist < mlen) ? (uint32_t)(65536.0f * __frcp_rn((float)dist)) + 2u : 0u;
+                    sts128(par_s + 16u * lane, m_pos, doomed ? 0u : mlen, dist, inv);
+                }
+                __syncwarp();
+                const uint32_t i1 = lane + 32;
+                uint4 nx = lds128(par_s + 16u * (uint32_t)(__ffs(dep) - 1));
+                uint32_t rest = dep;
+                for (;;) {
+                    rest &= rest - 1;
+                    const uint4 cu = nx;
+                    if (rest) nx = lds128(par_s + 16u * (uint32_t)(__ffs(rest) - 1));
+                    const uint32_t csa = cu.x - cu.z;
+                    const uint32_t k0 = lane - ((lane * cu.w) >> 16) * cu.z, k1 = i1 - ((i1 * cu.w) >> 16) * cu.z;
+                    if (lane < cu.y) sts8(out_s + ((cu.x + lane) & M), lds8(out_s + ((csa + k0) & M)));
+                    if (i1 < cu.y) sts8(out_s + ((cu.x + i1) & M), lds8(out_s + ((csa + k1) & M)));
+                    __syncwarp();
+                    if (!rest) break;
+                }
+                __threadfence_block();
+                if (has_match && !external) bits_set(bits_s, m_pos, mlen);
             }
             __syncwarp();
             flush_r2g(out_s, blk_out + (s_pos - base), s_pos, e_pos - s_pos);
         }
-        // ---- report completion (in-order retirement happens in the dispatcher)
+        // ---- report completion (retired in order by the dispatcher)
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) c->done[t & (kTickets - 1)] = t + 1;
+        if (lane == 0) vst(&ctl->done[k], t + 1);
     }
 }
 
@@ -579,8 +628,6 @@ decompress_kernel_wide(DecompressArgs a)
     WCtl* ctl = reinterpret_cast<WCtl*>(stages + kWC * kWStage);
     for (uint32_t i = threadIdx.x; i < sizeof(WCtl) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ctl)[i] = 0u;
     __syncthreads();
-    if (threadIdx.x == 0) ctl->s = -1;
-    __syncthreads();
     const int warp = (int)(threadIdx.x >> 5);
     uint4* garena = a.wide_arena + (size_t)blockIdx.x * (kWideArenaPerCta / 16);
     uint32_t out_s, bits_s;         // laundered so that the compiler keeps them in registers
@@ -589,8 +636,10 @@ decompress_kernel_wide(DecompressArgs a)
     if (warp < kWP)
         wparser_main(a, warp, ctl, smem_u32(in_rings) + (uint32_t)warp * kInRing, smem_u32(hdrs) + (uint32_t)warp * kWR * 16u,
                      garena + (size_t)warp * kWR * 32);
+    else if (warp == kWP)
+        wdispatch_main(a, ctl, out_s, bits_s, smem_u32(hdrs));
     else
-        wcopier_main(a, ctl, out_s, bits_s, smem_u32(hdrs), smem_u32(stages) + (uint32_t)(warp - kWP) * kWStage, garena);
+        wcopier_main(a, ctl, out_s, bits_s, smem_u32(stages) + (uint32_t)(warp - kWP - 1) * kWStage, garena);
 }
 
 }  // namespace
