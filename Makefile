@@ -26,11 +26,16 @@ $(GEN): $(PKG)/datagen/datagen.c
 oracle:
 	$(MAKE) -s -C oracle
 
+# development build with cycle accounting in the wide decoder (load it with B200LZ4_LIB=build/libb200lz4_stats.so)
+stats: $(CU_SRCS) $(CU_HDRS)
+	mkdir -p build
+	$(NVCC) $(NVFLAGS) -DB200LZ4_WIDE_STATS -shared -o build/libb200lz4_stats.so $(CU_SRCS) 2> build/ptxas_stats.log || (cat build/ptxas_stats.log; false)
+
 clean:
 	rm -f $(LIB) $(GEN) $(CSRC)/ptxas.log
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean stats
 
 # plain-C example over the C ABI (needs a B200 to run)
 examples: $(LIB)

@@ -36,18 +36,33 @@ using namespace dec;
 namespace {
 
 constexpr int kWP = kWideParsers;                 // parser warps
-constexpr int kWC = 7;                            // copier warps
+constexpr int kWC = 12;                           // copier warps
 constexpr int kWThreads = (kWP + 1 + kWC) * 32;   // + the dispatcher warp
 constexpr uint32_t kWOut = 131072, kWM = kWOut - 1;      // output ring (bytes), indexed by stream position
 constexpr int kWBitWords = kWOut / 32;            // one ready bit per ring byte
 constexpr int kWR = kWideRingBatches;             // batches per parser ring
-constexpr int kWStage = 1536;                     // per copier: staging of one batch's compressed bytes
+constexpr int kWStage = 1216;                     // per copier: staging of one batch's compressed bytes (32 x (token + 1 + 32 literals + offset + 1) + alignment)
+constexpr int kWIn = 2048;                        // per parser: input ring
 constexpr int kTickets = 64;                      // completion flags (ring)
 constexpr int kRunAhead = 61440;                  // a batch may end at most this far beyond the completion frontier
 constexpr uint32_t kPiece = 16384;                // long sequences are cut into pieces of this many output bytes
 constexpr uint32_t kSeedBase = 65536;             // stream position of the first output byte after (re)seeding
 
-struct WTicket { uint32_t jn, cf, op_start, base, valid_lo; int blk; uint32_t pad_[2]; };   // 32 bytes; jn = parser << 16 | ring slot
+// Cycle accounting for development builds (make stats -> build/libb200lz4_stats.so; tools/linked_probe.py --stats): every
+// warp adds its clock64() intervals to 64-bit counters in the scratch block's padding.  Compiled out of the product.
+#ifdef B200LZ4_WIDE_STATS
+#define WSTAT_DECL(n) unsigned long long wst_[n] = {0}; long long wst_t_ = clock64();
+#define WSTAT(i) { const long long now_ = clock64(); wst_[i] += (unsigned long long)(now_ - wst_t_); wst_t_ = now_; }
+#define WSTAT_COUNT(i) { wst_[i]++; }
+#define WSTAT_FLUSH(a, base, n) { if (lane_id() == 0) for (int q_ = 0; q_ < (n); q_++) atomicAdd(reinterpret_cast<unsigned long long*>((a).scratch->pad_) + (base) + q_, wst_[q_]); }
+#else
+#define WSTAT_DECL(n)
+#define WSTAT(i)
+#define WSTAT_COUNT(i)
+#define WSTAT_FLUSH(a, base, n)
+#endif
+
+struct WTicket { uint32_t jn, cf, op_start, base, valid_lo; int blk; uint32_t fpos, aux; };   // 32 bytes; jn = parser << 16 | ring slot
 
 struct WCtl {                                     // shared memory
     uint32_t next_ticket;                         // copiers draw tickets here (atomicAdd)
@@ -187,17 +202,21 @@ __device__ __forceinline__ void flush_r2g(uint32_t out_s, uint8_t* gdst, uint32_
     if (lane < tail) gdst[done + lane] = (uint8_t)lds8(rix(out_s, pos + done + lane));
 }
 
-// One match of at most 64 bytes copied by the whole warp (two bytes per lane).  Its source -- the dist bytes below dst,
-// or the len bytes from dst - dist on -- is complete; an overlapping match (dist < len) repeats those dist bytes:
-// byte i comes from source byte i mod dist, through a 16-bit fixed-point reciprocal that is exact for i < 64.
-__device__ __forceinline__ void coop_short_match(uint32_t out_s, uint32_t dst, uint32_t len, uint32_t dist)
+// One lane copies n bytes to ring position dst from shared address space `src_s` at byte offset `src` masked by
+// `smask` (the ring itself, or the staging buffer with an all-ones mask): four bytes per step (two aligned word loads, a
+// funnel shift, four byte stores that need not wait for each other), then the odd bytes.  The source may overlap the
+// destination from below by 4 bytes or more (an LZ4 match with offset >= 4).
+__device__ __forceinline__ void lane_copy4(uint32_t out_s, uint32_t dst, uint32_t src_s, uint32_t src, uint32_t smask, uint32_t n)
 {
-    const uint32_t lane = lane_id(), i1 = lane + 32u;
-    const uint32_t inv = (dist < len) ? (uint32_t)(65536.0f * __frcp_rn((float)dist)) + 2u : 0u;
-    const uint32_t src = dst - dist;
-    const uint32_t k0 = lane - ((lane * inv) >> 16) * dist, k1 = i1 - ((i1 * inv) >> 16) * dist;
-    if (lane < len) sts8(rix(out_s, dst + lane), lds8(rix(out_s, src + k0)));
-    if (i1 < len) sts8(rix(out_s, dst + i1), lds8(rix(out_s, src + k1)));
+    uint32_t i = 0;
+    for (; i + 4u <= n; i += 4u) {
+        const uint32_t a = src + i, al = a & ~3u;
+        const uint32_t w0 = lds32(src_s + (al & smask)), w1 = lds32(src_s + ((al + 4u) & smask));
+        const uint32_t v = __funnelshift_r(w0, w1, (a & 3u) * 8u);
+        sts8(rix(out_s, dst + i), v & 0xFFu); sts8(rix(out_s, dst + i + 1u), (v >> 8) & 0xFFu);
+        sts8(rix(out_s, dst + i + 2u), (v >> 16) & 0xFFu); sts8(rix(out_s, dst + i + 3u), v >> 24);
+    }
+    for (; i < n; i++) sts8(rix(out_s, dst + i), lds8(src_s + ((src + i) & smask)));
 }
 
 // A long match piece inside the ring, all lanes: rounds of one period each (the period's source is complete before
@@ -249,7 +268,7 @@ __device__ void wseed(uint32_t out_s, uint32_t bits_s, const uint8_t* tail_src, 
 // ------------------------------------------------------------------ parser sink ----
 struct WParser {
     static constexpr bool kWide = true;
-    static constexpr int kRing = kInRing;
+    static constexpr int kRing = kWIn;
     uint32_t ring_s;            // shared address of this parser's input ring
     const uint8_t* gbase;       // global address of ring-space position 0
     int end, issued_end, ready_end, cur_start;
@@ -260,11 +279,20 @@ struct WParser {
     int fill, flags;
     int op_start, op_end;       // block-relative output range of the batch being filled
     int need;                   // bytes before the block start the furthest-reaching match reads (deferred cbits/lz4.c:2073)
+#ifdef B200LZ4_WIDE_STATS
+    unsigned long long ring_wait = 0;
+#endif
 
     __device__ __forceinline__ uint32_t at(int p) const { return lds8(ring_s + ((uint32_t)p & (kRing - 1))); }
     __device__ __forceinline__ void begin()
     {   // the ring slot of this batch must have been retired
-        while (batch - vld(cons) >= (uint32_t)kWR) __nanosleep(200);
+#ifdef B200LZ4_WIDE_STATS
+        const long long w0_ = clock64();
+#endif
+        while (batch - vld(cons) >= (uint32_t)kWR) __nanosleep(2000);      // (a full ring is >= 200 us of copier work)
+#ifdef B200LZ4_WIDE_STATS
+        ring_wait += (unsigned long long)(clock64() - w0_);
+#endif
         fill = 0;
     }
     __device__ __forceinline__ uint4* slot() const { return gring + (size_t)(batch & (kWR - 1)) * 32; }
@@ -283,8 +311,14 @@ struct WParser {
         if (extra & kEndBlock) cp_async_wait_all();      // nothing of this block's input may land after the next block starts
         __threadfence();                                 // descriptor stores (several lanes) before the header
         __syncwarp();
+        uint32_t aux = (uint32_t)need;
+        if (!(extra & (kEndBlock | kBulk))) {            // where the batch's literals lie: [cur_start, ip) of the payload, in 16-byte vectors
+            const uint32_t lo = (uint32_t)cur_start & ~15u, nv = ((uint32_t)ip - lo + 15u) >> 4;
+            aux = lo;
+            if (nv <= (uint32_t)(kWStage / 16)) cf |= nv << 8;
+        }
         if (lane_id() == 0) {
-            sts128(hdr_s + 16u * (batch & (kWR - 1)), cf, (uint32_t)op_start, (uint32_t)op_end, (extra & kEndBlock) ? (uint32_t)need : 0u);
+            sts128(hdr_s + 16u * (batch & (kWR - 1)), cf, (uint32_t)op_start, (uint32_t)op_end, aux);
             __threadfence_block();
             vst(wr_pub, batch + 1);
         }
@@ -312,8 +346,8 @@ struct WParser {
         }
     }
     __device__ __forceinline__ void top_up(int ip)
-    {   // only this warp reads its ring, and it never looks back more than a window: 2.5 KiB ahead always fits 4 KiB
-        while (issued_end < end && issued_end - ip < 2048) {
+    {   // only this warp reads its ring, and it never looks back: 1.5 KiB ahead always fits the 2 KiB ring
+        while (issued_end < end && issued_end - ip < 1024) {
             const int p = issued_end + 16 * (int)lane_id();
             if (p < end) cp_async_16(ring_s + ((uint32_t)p & (kRing - 1)), gbase + p);
             cp_async_commit();
@@ -341,6 +375,9 @@ __device__ void wparser_main(const DecompressArgs& a, int j, WCtl* ctl, uint32_t
     P.ring_s = ring_s; P.gbase = nullptr; P.end = P.issued_end = P.ready_end = P.cur_start = 0;
     P.gring = gring; P.hdr_s = hdr_s; P.wr_pub = &ctl->wr_pub[j]; P.cons = &ctl->cons[j];
     P.batch = 0; P.fill = 0; P.flags = 0; P.op_start = P.op_end = 0; P.need = 0;
+#ifdef B200LZ4_WIDE_STATS
+    const long long p0_ = clock64();
+#endif
     for (int s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
         const int b0 = a.stream_first ? a.stream_first[s] : a.first_block + s;
         const int b1 = a.stream_first ? a.stream_first[s + 1] : b0 + 1;
@@ -356,6 +393,12 @@ __device__ void wparser_main(const DecompressArgs& a, int j, WCtl* ctl, uint32_t
             P.publish(kEndBlock, r, 0);
         }
     }
+#ifdef B200LZ4_WIDE_STATS
+    if (lane_id() == 0) {
+        unsigned long long* st = reinterpret_cast<unsigned long long*>(a.scratch->pad_);
+        atomicAdd(st + 0, (unsigned long long)(clock64() - p0_)); atomicAdd(st + 1, P.ring_wait); atomicAdd(st + 2, (unsigned long long)P.batch);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------ dispatcher ----
@@ -386,11 +429,13 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
 {
     const uint32_t lane = lane_id();
     WDispatch D{ctl, 0u, 0u, kSeedBase};
+    WSTAT_DECL(4)       // 0 other, 1 waiting for the parser, 2 waiting for flow control, 3 stream open / close
     for (int s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
         const int b0 = a.stream_first ? a.stream_first[s] : a.first_block + s;
         const int b1 = a.stream_first ? a.stream_first[s + 1] : b0 + 1;
         DState* st = a.states ? reinterpret_cast<DState*>(a.states[s]) : nullptr;
         // ---- open the stream: the ring restarts at kSeedBase with the kept tail of the previous call as dictionary
+        WSTAT(0)
         D.drain();
         uint32_t dict_len = 0, kept = 0;
         if (st && st->prev_len) { dict_len = st->prev_len; kept = st->kept; wseed(out_s, bits_s, st->tail + 65536 - kept, kept); }
@@ -398,11 +443,14 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
         uint32_t base = kSeedBase, valid_lo = kSeedBase - kept;
         D.fpos = kSeedBase;
         const uint8_t* last_out = nullptr; int last_len = 0;
+        WSTAT(3)
         for (int blk = b0; blk < b1; blk++) {
             const uint32_t j = (uint32_t)(blk - b0) % (uint32_t)kWP;
             for (;;) {                                                      // the batches of this block, in order
                 const uint32_t n = vld(&ctl->rd[j]);
+                WSTAT(0)
                 while (vld(&ctl->wr_pub[j]) == n) { D.advance(); __nanosleep(20); }    // (retiring slots may be what a parser waits for)
+                WSTAT(1)
                 __threadfence_block();
                 const uint4 h = lds128(hdrs_s + (j * kWR + (n & (kWR - 1))) * 16u);
                 const uint32_t e = base + h.z;
@@ -413,11 +461,12 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
                     if ((int)(e - D.fpos) <= kRunAhead && D.T - D.F < (uint32_t)(kTickets - 16)) break;
                     __nanosleep(20);
                 }
+                WSTAT(2)
                 const uint32_t k = D.T & (kTickets - 1);
                 vst(&ctl->tend[k], e); vst(&ctl->tj[k], j); vst(&ctl->tn[k], n);
                 if (lane == 0) {
                     WTicket* tk = &ctl->ticket[k];
-                    tk->jn = (j << 16) | (n & (kWR - 1)); tk->cf = h.x; tk->op_start = h.y; tk->base = base; tk->valid_lo = valid_lo; tk->blk = blk;
+                    tk->jn = (j << 16) | (n & (kWR - 1)); tk->cf = h.x; tk->op_start = h.y; tk->base = base; tk->valid_lo = valid_lo; tk->blk = blk; tk->fpos = D.fpos; tk->aux = h.w;
                     __threadfence_block();
                     vst(&ctl->tready[k], D.T + 1);
                 }
@@ -461,6 +510,8 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
     }
     D.drain();
     vst(&ctl->finished, 1u);
+    WSTAT(3)
+    WSTAT_FLUSH(a, 4, 4)
 }
 
 // ---------------------------------------------------------------------- copiers ----
@@ -469,6 +520,7 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
     constexpr uint32_t M = kWM;
     const uint32_t lane = lane_id();
     int cached_blk = -1; uint8_t* blk_out = nullptr; const uint8_t* blk_gbase = nullptr;
+    WSTAT_DECL(10)      // 0 waiting for a ticket, 1 loads, 2 literals, 3 phase X waiting, 4 phase X copying, 5 straddle wait, 6 phase I, 7 flush + done, 8 bulk, 9 tickets
     for (;;) {
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(&ctl->next_ticket, 1u);
@@ -477,14 +529,16 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
         bool fin = false;
         while (vld(&ctl->tready[k]) != t + 1) { if (vld(&ctl->finished)) { fin = true; break; } __nanosleep(20); }
         if (fin) break;
+        WSTAT(0) WSTAT_COUNT(9)
         __threadfence_block();
-        const uint4 tk = lds128(smem_u32(&ctl->ticket[k]));
-        const uint32_t valid_lo = vld(&ctl->ticket[k].valid_lo);
-        const int blk = (int)vld(reinterpret_cast<const uint32_t*>(&ctl->ticket[k].blk));
+        const uint4 tk = lds128(smem_u32(&ctl->ticket[k])), tk2 = lds128(smem_u32(&ctl->ticket[k]) + 16u);
+        const uint32_t valid_lo = tk2.x, fpos_t = tk2.z, lo_h = tk2.w;
+        const int blk = (int)tk2.y;
         const uint32_t j = tk.x >> 16, slot = tk.x & 0xFFFFu, base = tk.w, op_start = tk.z;
         const int cf = (int)tk.y;
 
-        const int cnt = cf & kCountMask;
+        const int cnt = cf & 0xFF;
+        const uint32_t nvec_h = ((uint32_t)cf >> 8) & 0xFFu;                 // 16-byte vectors of compressed input the batch's literals lie in (0: not given)
         uint4 d = make_uint4(0, 0, 0, 0);
         if ((int)lane < cnt) d = ld_cg_128(garena + ((size_t)j * kWR + slot) * 32 + lane);
         if (blk != cached_blk) {
@@ -518,22 +572,21 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
                 bits_set_coop(bits_s, m_pos, mlen);
                 flush_r2g(out_s, gout + lit, m_pos, mlen);
             }
+            WSTAT(8)
         } else if (cnt) {
             // ---- up to 32 short sequences, one per lane
-            const bool is_seq = (int)lane < cnt;
-            const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
-            const uint32_t lit_pos = base + d.z, m_pos = lit_pos + lit, from = m_pos - dist;
-            const uint32_t s_pos = __shfl_sync(kFull, lit_pos, 0);
-            const uint32_t e_pos = __shfl_sync(kFull, m_pos + mlen, cnt - 1);
-            // the batch's compressed bytes (its literals lie between the first literal start and the last literal end):
-            // one coalesced 128-bit pass into this warp's staging buffer
-            const uint32_t lo = __shfl_sync(kFull, d.x, 0) & ~15u;
-            const uint32_t hi = __shfl_sync(kFull, d.x + lit, cnt - 1);
-            const uint32_t nvec = (hi - lo + 15u) >> 4;
+            // the batch's compressed bytes: one coalesced 128-bit pass into this warp's staging buffer.  The parser put the
+            // range into the batch header, so these loads are in flight together with the descriptor load above
+            // (a block's last batch carries no range: take it from the descriptors).
+            uint32_t lo = lo_h, nvec = nvec_h;
+            if (nvec == 0) {
+                lo = __shfl_sync(kFull, d.x, 0) & ~15u;
+                nvec = (__shfl_sync(kFull, d.x + (d.y & 0xFFu), cnt - 1) - lo + 15u) >> 4;
+            }
             const bool staged = nvec <= (uint32_t)(kWStage / 16);
             if (staged) {
                 const uint4* gv = reinterpret_cast<const uint4*>(blk_gbase + lo);
-                uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, x2 = x0;       // (at most 96 vectors: three per lane, all in flight at once)
+                uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, x2 = x0;       // (at most 76 vectors: three per lane, all in flight at once)
                 if (lane < nvec) x0 = ldg_na_u128(gv + lane);
                 if (lane + 32u < nvec) x1 = ldg_na_u128(gv + lane + 32u);
                 if (lane + 64u < nvec) x2 = ldg_na_u128(gv + lane + 64u);
@@ -541,11 +594,16 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
                 if (lane + 32u < nvec) sts128(stage_s + 16u * (lane + 32u), x1.x, x1.y, x1.z, x1.w);
                 if (lane + 64u < nvec) sts128(stage_s + 16u * (lane + 64u), x2.x, x2.y, x2.z, x2.w);
             }
+            const bool is_seq = (int)lane < cnt;
+            const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
+            const uint32_t lit_pos = base + d.z, m_pos = lit_pos + lit, from = m_pos - dist;
+            const uint32_t s_pos = __shfl_sync(kFull, lit_pos, 0);
+            const uint32_t e_pos = __shfl_sync(kFull, m_pos + mlen, cnt - 1);
             __syncwarp();
+            WSTAT(1)
             if (is_seq && lit) {
                 if (staged) {
-                    const uint32_t sl = stage_s + (d.x - lo);
-                    for (uint32_t i = 0; i < lit; i++) sts8(out_s + ((lit_pos + i) & M), lds8(sl + i));
+                    lane_copy4(out_s, lit_pos, stage_s, d.x - lo, 0xFFFFFFFFu, lit);
                 } else {
                     const uint8_t* gp = blk_gbase + d.x;
                     for (uint32_t i = 0; i < lit; i++) sts8(out_s + ((lit_pos + i) & M), (uint32_t)__ldg(gp + i));
@@ -559,15 +617,21 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
             // phase X: matches whose source lies wholly before this batch (other warps' output): whichever are ready, lane-parallel
             const bool external = has_match && (int)(from + need_n - s_pos) <= 0;
             bool pend = external;
+            WSTAT(2)
             while (__ballot_sync(kFull, pend)) {
-                const bool rdy = pend && (doomed || bits_ready(bits_s, from, need_n));
+                // (everything below the completion frontier the ticket was issued at is final: no need to look at its bits)
+                const bool rdy = pend && (doomed || (int)(from + need_n - fpos_t) <= 0 || bits_ready(bits_s, from, need_n));
                 if (__ballot_sync(kFull, rdy)) {
                     __threadfence_block();
-                    if (rdy && !doomed) for (uint32_t i = 0; i < mlen; i++) sts8(out_s + ((m_pos + i) & M), lds8(out_s + ((from + i) & M)));
+                    if (rdy && !doomed) {
+                        if (dist >= 4u) lane_copy4(out_s, m_pos, out_s, from, M, mlen);
+                        else for (uint32_t i = 0; i < mlen; i++) sts8(out_s + ((m_pos + i) & M), lds8(out_s + ((from + i) & M)));
+                    }
                     __threadfence_block();
                     if (rdy) bits_set(bits_s, m_pos, mlen);
                     pend = pend && !rdy;
-                } else __nanosleep(20);
+                    WSTAT(4)
+                } else { __nanosleep(20); WSTAT(3) }
             }
             // phase I: matches that read bytes of this batch, in order, each copied by all lanes (the narrow kernel's phase B).
             // A source may start up to 64 bytes below the batch: those bytes belong to earlier tickets and must be complete.
@@ -575,10 +639,11 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
             if (dep) {
                 const int below = (has_match && !external && !doomed) ? (int)(s_pos - from) : 0;      // > 0: reads that many bytes below the batch
                 const int reach = __reduce_max_sync(kFull, below);
-                if (reach > 0) {
+                if (reach > 0 && (int)(s_pos - fpos_t) > 0) {
                     while (!bits_ready_coop(bits_s, s_pos - (uint32_t)reach, (uint32_t)reach)) __nanosleep(20);
                     __threadfence_block();
                 }
+                WSTAT(5)
                 __syncwarp();
                 const uint32_t par_s = stage_s;                             // (the staged input has been consumed)
                 {
@@ -602,6 +667,7 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
                 }
                 __threadfence_block();
                 if (has_match && !external) bits_set(bits_s, m_pos, mlen);
+                WSTAT(6)
             }
             __syncwarp();
             flush_r2g(out_s, blk_out + (s_pos - base), s_pos, e_pos - s_pos);
@@ -610,10 +676,12 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
         __threadfence_block();
         __syncwarp();
         if (lane == 0) vst(&ctl->done[k], t + 1);
+        WSTAT(7)
     }
+    WSTAT_FLUSH(a, 8, 10)
 }
 
-constexpr size_t kWSmem = 128 /* alignment slack */ + kWOut + kWBitWords * 4 + kWP * kInRing + kWP * kWR * 16 + kWC * kWStage + sizeof(WCtl);
+constexpr size_t kWSmem = 128 /* alignment slack */ + kWOut + kWBitWords * 4 + kWP * kWIn + kWP * kWR * 16 + kWC * kWStage + sizeof(WCtl);
 
 __global__ void __launch_bounds__(kWThreads, 1)
 decompress_kernel_wide(DecompressArgs a)
@@ -623,7 +691,7 @@ decompress_kernel_wide(DecompressArgs a)
     uint8_t* out_ring = base;
     uint8_t* bits = out_ring + kWOut;
     uint8_t* in_rings = bits + kWBitWords * 4;
-    uint8_t* hdrs = in_rings + kWP * kInRing;
+    uint8_t* hdrs = in_rings + kWP * kWIn;
     uint8_t* stages = hdrs + kWP * kWR * 16;
     WCtl* ctl = reinterpret_cast<WCtl*>(stages + kWC * kWStage);
     for (uint32_t i = threadIdx.x; i < sizeof(WCtl) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ctl)[i] = 0u;
@@ -634,7 +702,7 @@ decompress_kernel_wide(DecompressArgs a)
     asm volatile("mov.u32 %0, %1;" : "=r"(out_s) : "r"(smem_u32(out_ring)));
     asm volatile("mov.u32 %0, %1;" : "=r"(bits_s) : "r"(smem_u32(bits)));
     if (warp < kWP)
-        wparser_main(a, warp, ctl, smem_u32(in_rings) + (uint32_t)warp * kInRing, smem_u32(hdrs) + (uint32_t)warp * kWR * 16u,
+        wparser_main(a, warp, ctl, smem_u32(in_rings) + (uint32_t)warp * kWIn, smem_u32(hdrs) + (uint32_t)warp * kWR * 16u,
                      garena + (size_t)warp * kWR * 32);
     else if (warp == kWP)
         wdispatch_main(a, ctl, out_s, bits_s, smem_u32(hdrs));

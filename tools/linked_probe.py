@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--kinds", default="mixed,text")
     ap.add_argument("--accel", type=int, default=1)
     ap.add_argument("--block", type=int, default=65536)
+    ap.add_argument("--stats", action="store_true", help="print the wide decoder's cycle counters (needs the stats build)")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda", 0)
@@ -61,7 +62,13 @@ def main():
                                                 p(d_blen), 8, 0, p(scratch), sh)
                 assert rc == 0
             dec(); torch.cuda.synchronize()
+            scratch[:256].zero_()
             e[0].record(stream); dec(); e[1].record(stream); torch.cuda.synchronize()
+            if args.stats:
+                st = scratch[16:256].cpu().numpy().view(np.uint64)
+                names = ["parser total", "parser ring wait", "batches", "-", "disp other", "disp wait parser", "disp wait flow", "disp open/close",
+                         "cop wait ticket", "cop loads", "cop literals", "cop X wait", "cop X copy", "cop straddle wait", "cop phase I", "cop flush", "cop bulk", "tickets"]
+                print("   stats (Mcycles summed over warps): " + ", ".join(f"{n}={int(v) / 1e6:.1f}" for n, v in zip(names, st)))
             dms = e[0].elapsed_time(e[1])
             ok = bool(torch.equal(d_back[:total], d_src))
             print(f"{kind:8s} {ns:7d} {args.mib_per_stream:7d} {total / ctot:6.2f} {cms:9.2f} {total / cms / 1e6:10.2f} {per / cms / 1e3:11.1f} "
