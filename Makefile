@@ -5,7 +5,8 @@ CXX    ?= g++
 PKG    := streamly_lz4_b200
 CSRC   := $(PKG)/csrc
 ARCH   := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v -Iinclude -I$(CSRC)
+EXTRA  ?=
+NVFLAGS := $(EXTRA) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v -Iinclude -I$(CSRC)
 
 LIB    := $(PKG)/libb200lz4.so
 GEN    := $(PKG)/datagen/libb200gen.so
@@ -29,7 +30,7 @@ oracle:
 # development build with cycle accounting in the wide decoder (load it with B200LZ4_LIB=build/libb200lz4_stats.so)
 stats: $(CU_SRCS) $(CU_HDRS)
 	mkdir -p build
-	$(NVCC) $(NVFLAGS) -DB200LZ4_WIDE_STATS -shared -o build/libb200lz4_stats.so $(CU_SRCS) 2> build/ptxas_stats.log || (cat build/ptxas_stats.log; false)
+	$(NVCC) $(NVFLAGS) -DB200LZ4_WIDE_STATS -shared -o build/libb200lz4_stats$(SUFFIX).so $(CU_SRCS) 2> build/ptxas_stats.log || (cat build/ptxas_stats.log; false)
 
 clean:
 	rm -f $(LIB) $(GEN) $(CSRC)/ptxas.log

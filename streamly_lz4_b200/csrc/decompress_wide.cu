@@ -13,18 +13,23 @@
 //                    64 KiB block: L2-resident) and a 16-byte batch header into a shared-memory ring.
 //   1 DISPATCHER warp hands batches out strictly in stream order as numbered tickets (which parser's ring is next, the
 //                    batch's absolute output position, flow control, in-order retirement, stream begin / end).
-//   7 COPIER warps   draw tickets and EXECUTE them out of order.  The
-//                    stream's last 128 KiB of output live in a shared-memory ring indexed by stream position, with one
-//                    READY bit per byte (lap parity, so bits never need clearing): literals are copied at once, a
-//                    match waits (spinning on the bits) only for the bytes it really reads, then publishes its own.
-//                    Matches whose source lies before the batch are copied lane-parallel as they become ready; matches
-//                    that read the batch's own output (records, runs: a dependency chain) then run in order, one
-//                    warp-cooperative copy per link, exactly like the narrow kernel's phase B.  Every warp flushes its
-//                    own batch to global memory with 128-bit stores.
+//   10 COPIER warps  in four roles that form a pipeline over the tickets.  The stream's last 128 KiB of output live in a
+//                    shared-memory ring indexed by stream position.
+//       L (3 warps)  literals: descriptor batch -> shared memory, the batch's compressed bytes -> staging (one coalesced
+//                    pass, range given by the parser), every lane copies the literals of its sequence into the ring.
+//                    No dependencies at all, so L runs ahead.
+//       F (4 warps)  FAR matches, lane-parallel: a match of ticket t whose source ends below the start of ticket t - 2
+//                    only reads bytes that are final once the serial stage has finished ticket t - 3.
+//       N (1 warp)   NEAR matches (everything else: sources inside the last two batches, overlapping runs, records), in
+//                    stream order, each copied by all 32 lanes -- the narrow kernel's phase B.  This is the stream's one
+//                    serial chain; it carries only the matches that really depend on recent output.  Long match pieces
+//                    run here too.
+//       G (2 warps)  flush finished batches to global memory with 128-bit stores and report completion.
 //
 // Flow control: a batch may only be handed out while its end is less than 60 KiB ahead of the in-order completion
-// frontier (the ring holds 128 KiB, matches reach 64 KiB back); long sequences are cut into pieces of 16 KiB by the
-// parser so that every batch is small against that window.
+// frontier (the ring holds 128 KiB, matches reach 64 KiB back) and fewer than 16 tickets are in flight (their descriptor
+// batches sit in shared memory); long sequences are cut into pieces of 16 KiB by the parser so that every batch is small
+// against that window.
 #include <cstdlib>
 #include <mutex>
 #include "decode_common.cuh"
@@ -36,10 +41,15 @@ using namespace dec;
 namespace {
 
 constexpr int kWP = kWideParsers;                 // parser warps
-constexpr int kWC = 12;                           // copier warps
+constexpr int kWL = 3, kWF = 4, kWG = 2;           // copier warps per role: literals, far matches, flush (+ one serial warp N)
+constexpr int kWC = kWL + kWF + 1 + kWG;
 constexpr int kWThreads = (kWP + 1 + kWC) * 32;   // + the dispatcher warp
+#ifndef B200LZ4_WIDE_DEPTH
+#define B200LZ4_WIDE_DEPTH 2
+#endif
+constexpr int kWDepth = B200LZ4_WIDE_DEPTH;       // a match is FAR if its source ends below the start of the ticket kWDepth before its own
+constexpr int kWSlots = 16;                       // descriptor batches resident in shared memory = tickets in flight
 constexpr uint32_t kWOut = 131072, kWM = kWOut - 1;      // output ring (bytes), indexed by stream position
-constexpr int kWBitWords = kWOut / 32;            // one ready bit per ring byte
 constexpr int kWR = kWideRingBatches;             // batches per parser ring
 constexpr int kWStage = 1216;                     // per copier: staging of one batch's compressed bytes (32 x (token + 1 + 32 literals + offset + 1) + alignment)
 constexpr int kWIn = 2048;                        // per parser: input ring
@@ -62,17 +72,19 @@ constexpr uint32_t kSeedBase = 65536;             // stream position of the firs
 #define WSTAT_FLUSH(a, base, n)
 #endif
 
-struct WTicket { uint32_t jn, cf, op_start, base, valid_lo; int blk; uint32_t fpos, aux; };   // 32 bytes; jn = parser << 16 | ring slot
+struct WTicket { uint32_t jn, cf, op_start, base, valid_lo; int blk; uint32_t safe, aux; };   // 32 bytes; jn = parser << 16 | ring slot; safe: everything below is final for stage F
 
 struct WCtl {                                     // shared memory
-    uint32_t next_ticket;                         // copiers draw tickets here (atomicAdd)
+    uint32_t near_next;                           // stage N: tickets below this are complete in the ring
     uint32_t finished;                            // dispatcher: no more tickets will be issued
-    uint32_t pad_[2];
+    uint32_t t_final;                             // ... and this many were
+    uint32_t pad_;
     uint32_t rd[kWP];                             // dispatcher: next batch of each parser ring to hand out
     uint32_t wr_pub[kWP];                         // parsers: batches published
     uint32_t cons[kWP];                           // dispatcher: batches retired (parsers wait on it for ring space)
     uint32_t tready[kTickets];                    // dispatcher: ticket t issued <=> tready[t % 64] == t + 1
-    uint32_t done[kTickets];                      // copiers: ticket t complete <=> done[t % 64] == t + 1
+    uint32_t lit_done[kTickets], far_done[kTickets];      // stages L / F: ticket t done <=> flag[t % 64] == t + 1
+    uint32_t done[kTickets];                      // stage G: ticket t is in global memory <=> done[t % 64] == t + 1
     uint32_t tend[kTickets], tn[kTickets], tj[kTickets];      // dispatcher-private: end position / ring slot / parser of a ticket
     WTicket ticket[kTickets];
 };
@@ -81,70 +93,8 @@ __device__ __forceinline__ uint32_t vld(const uint32_t* p) { return *reinterpret
 __device__ __forceinline__ void vst(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void red_or(uint32_t a, uint32_t m) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(m) : "memory"); }
-__device__ __forceinline__ void red_and(uint32_t a, uint32_t m) { asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(m) : "memory"); }
 __device__ __forceinline__ uint4 ld_cg_128(const uint4* p)
 { uint4 v; asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v; }
-
-// ---------------------------------------------------------------- ready bits ----
-// Bit i of word (pos >> 5) & 4095 belongs to ring byte pos & 131071.  A byte written on lap L = pos >> 17 sets its bit
-// to L & 1; a reader that wants position pos expects (pos >> 17) & 1.  What the previous lap left behind has the other
-// parity, so bits are never cleared; the run-ahead rule keeps a writer from lapping a reader.
-__device__ __forceinline__ uint32_t bit_addr(uint32_t bits_s, uint32_t pos) { return bits_s + (((pos >> 5) & (kWBitWords - 1)) << 2); }
-
-__device__ __forceinline__ void bits_set(uint32_t bits_s, uint32_t pos, uint32_t n)          // per lane, short ranges
-{
-    const uint32_t end = pos + n;
-    while (pos != end) {
-        const uint32_t lo = pos & 31u, cnt = min(32u - lo, end - pos);
-        const uint32_t mask = (cnt == 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << lo;
-        if ((pos >> 17) & 1u) red_or(bit_addr(bits_s, pos), mask); else red_and(bit_addr(bits_s, pos), ~mask);
-        pos += cnt;
-    }
-}
-__device__ __forceinline__ bool bits_ready(uint32_t bits_s, uint32_t pos, uint32_t n)        // per lane, short ranges
-{
-    const uint32_t end = pos + n;
-    bool ok = true;
-    while (pos != end) {
-        const uint32_t lo = pos & 31u, cnt = min(32u - lo, end - pos);
-        const uint32_t mask = (cnt == 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << lo;
-        const uint32_t want = ((pos >> 17) & 1u) ? 0xFFFFFFFFu : 0u;
-        ok = ok && ((((lds32(bit_addr(bits_s, pos)) ^ ~want) & mask)) == mask);
-        pos += cnt;
-    }
-    return ok;
-}
-// the same for long ranges, all lanes together (words strided over the lanes; position arithmetic may wrap at 2^32)
-__device__ __forceinline__ void bits_set_coop(uint32_t bits_s, uint32_t pos, uint32_t n)
-{
-    if (n == 0) return;
-    const uint32_t last = pos + n - 1u, w0 = pos >> 5;
-    const uint32_t count = (((last >> 5) - w0) & 0x07FFFFFFu) + 1u;
-    for (uint32_t k = lane_id(); k < count; k += 32) {
-        const uint32_t w = w0 + k;
-        const uint32_t lo = (k == 0) ? (pos & 31u) : 0u, hi = (k == count - 1u) ? (last & 31u) : 31u;
-        const uint32_t mask = (hi - lo == 31u) ? 0xFFFFFFFFu : (((1u << (hi - lo + 1u)) - 1u) << lo);
-        const uint32_t a = bits_s + ((w & (kWBitWords - 1)) << 2);
-        if ((w >> 12) & 1u) red_or(a, mask); else red_and(a, ~mask);
-    }
-}
-__device__ __forceinline__ bool bits_ready_coop(uint32_t bits_s, uint32_t pos, uint32_t n)
-{
-    bool ok = true;
-    if (n) {
-        const uint32_t last = pos + n - 1u, w0 = pos >> 5;
-        const uint32_t count = (((last >> 5) - w0) & 0x07FFFFFFu) + 1u;
-        for (uint32_t k = lane_id(); k < count; k += 32) {
-            const uint32_t w = w0 + k;
-            const uint32_t lo = (k == 0) ? (pos & 31u) : 0u, hi = (k == count - 1u) ? (last & 31u) : 31u;
-            const uint32_t mask = (hi - lo == 31u) ? 0xFFFFFFFFu : (((1u << (hi - lo + 1u)) - 1u) << lo);
-            const uint32_t want = ((w >> 12) & 1u) ? 0xFFFFFFFFu : 0u;
-            ok = ok && (((lds32(bits_s + ((w & (kWBitWords - 1)) << 2)) ^ ~want) & mask) == mask);
-        }
-    }
-    return __all_sync(kFull, ok);
-}
 
 // ------------------------------------------------------------- ring <-> global ----
 __device__ __forceinline__ uint32_t rix(uint32_t out_s, uint32_t pos) { return out_s + (pos & kWM); }
@@ -250,16 +200,9 @@ __device__ __forceinline__ void coop_long_match(uint32_t out_s, uint32_t dst, ui
     }
 }
 
-// (re)start the ring at stream position kSeedBase: ready bits for lap 0 -- the lower half (which may hold the
-// dictionary, right-aligned below kSeedBase) reads as complete, the upper half as not yet written -- then the
-// dictionary bytes themselves.
-__device__ void wseed(uint32_t out_s, uint32_t bits_s, const uint8_t* tail_src, uint32_t kept)
+// (re)start the ring at stream position kSeedBase: the dictionary (at most 64 KiB) lies right-aligned below it
+__device__ void wseed(uint32_t out_s, const uint8_t* tail_src, uint32_t kept)
 {
-    const uint32_t lane = lane_id();
-    for (uint32_t i = lane; i < kWBitWords / 4; i += 32) {
-        const uint32_t v = (i < kWBitWords / 8) ? 0u : 0xFFFFFFFFu;
-        sts128(bits_s + 16u * i, v, v, v, v);
-    }
     if (kept) copy_g2r<false>(out_s, kSeedBase - kept, tail_src, kept);
     __threadfence_block();
     __syncwarp();
@@ -425,7 +368,7 @@ struct WDispatch {
     }
 };
 
-__device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, uint32_t bits_s, uint32_t hdrs_s)
+__device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, uint32_t hdrs_s)
 {
     const uint32_t lane = lane_id();
     WDispatch D{ctl, 0u, 0u, kSeedBase};
@@ -438,10 +381,13 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
         WSTAT(0)
         D.drain();
         uint32_t dict_len = 0, kept = 0;
-        if (st && st->prev_len) { dict_len = st->prev_len; kept = st->kept; wseed(out_s, bits_s, st->tail + 65536 - kept, kept); }
-        else wseed(out_s, bits_s, nullptr, 0u);
+        if (st && st->prev_len) { dict_len = st->prev_len; kept = st->kept; wseed(out_s, st->tail + 65536 - kept, kept); }
+        else wseed(out_s, nullptr, 0u);
         uint32_t base = kSeedBase, valid_lo = kSeedBase - kept;
         D.fpos = kSeedBase;
+        uint32_t hist[kWDepth];                                          // start positions of the last kWDepth tickets (nothing in flight: all final)
+        #pragma unroll
+        for (int q = 0; q < kWDepth; q++) hist[q] = kSeedBase;
         const uint8_t* last_out = nullptr; int last_len = 0;
         WSTAT(3)
         for (int blk = b0; blk < b1; blk++) {
@@ -458,7 +404,7 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
                 // 60 KiB beyond the completion frontier; ticket slots are reused after 64
                 for (;;) {
                     D.advance();
-                    if ((int)(e - D.fpos) <= kRunAhead && D.T - D.F < (uint32_t)(kTickets - 16)) break;
+                    if ((int)(e - D.fpos) <= kRunAhead && D.T - D.F < (uint32_t)(kWSlots - 1)) break;
                     __nanosleep(20);
                 }
                 WSTAT(2)
@@ -466,13 +412,16 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
                 vst(&ctl->tend[k], e); vst(&ctl->tj[k], j); vst(&ctl->tn[k], n);
                 if (lane == 0) {
                     WTicket* tk = &ctl->ticket[k];
-                    tk->jn = (j << 16) | (n & (kWR - 1)); tk->cf = h.x; tk->op_start = h.y; tk->base = base; tk->valid_lo = valid_lo; tk->blk = blk; tk->fpos = D.fpos; tk->aux = h.w;
+                    tk->jn = (j << 16) | (n & (kWR - 1)); tk->cf = h.x; tk->op_start = h.y; tk->base = base; tk->valid_lo = valid_lo; tk->blk = blk; tk->safe = hist[kWDepth - 1]; tk->aux = h.w;
                     __threadfence_block();
                     vst(&ctl->tready[k], D.T + 1);
                 }
                 __syncwarp();
                 D.T++;
                 vst(&ctl->rd[j], n + 1);
+                #pragma unroll
+                for (int q = kWDepth - 1; q > 0; q--) hist[q] = hist[q - 1];
+                hist[0] = base + h.y;
                 if ((int)h.x & kEndBlock) {
                     int r = ((int)h.x & kFailed) ? -1 : (int)h.z;
                     if (r >= 0 && dict_len < 65536u && h.w > dict_len) r = -1;      // cbits/lz4.c:2073, deferred: a match reached below the dictionary
@@ -488,12 +437,14 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
                         kept = 0; dict_len = 0;
                         if (last_out) {
                             dict_len = (uint32_t)last_len; kept = dict_len < 65536u ? dict_len : 65536u;
-                            wseed(out_s, bits_s, last_out + last_len - kept, kept);
+                            wseed(out_s, last_out + last_len - kept, kept);
                         } else if (st && st->prev_len) {
                             dict_len = st->prev_len; kept = st->kept;
-                            wseed(out_s, bits_s, st->tail + 65536 - kept, kept);
-                        } else wseed(out_s, bits_s, nullptr, 0u);
+                            wseed(out_s, st->tail + 65536 - kept, kept);
+                        } else wseed(out_s, nullptr, 0u);
                         base = kSeedBase; valid_lo = kSeedBase - kept; D.fpos = kSeedBase;
+                        #pragma unroll
+                        for (int q = 0; q < kWDepth; q++) hist[q] = kSeedBase;
                     }
                     break;
                 }
@@ -509,79 +460,68 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
         }
     }
     D.drain();
+    vst(&ctl->t_final, D.T);
+    __threadfence_block();
     vst(&ctl->finished, 1u);
     WSTAT(3)
     WSTAT_FLUSH(a, 4, 4)
 }
 
 // ---------------------------------------------------------------------- copiers ----
-__device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, uint32_t bits_s, uint32_t stage_s, const uint4* garena)
+// wait until flag[t % 64] == t + 1
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t t)
+{ while (vld(&flag[t & (kTickets - 1)]) != t + 1) __nanosleep(20); __threadfence_block(); }
+// wait until ticket t has been issued; false: the dispatcher has finished and never issued it
+__device__ __forceinline__ bool wait_ticket(WCtl* ctl, uint32_t t)
+{
+    while (vld(&ctl->tready[t & (kTickets - 1)]) != t + 1) {
+        if (vld(&ctl->finished) && (int)(t - vld(&ctl->t_final)) >= 0) return false;
+        __nanosleep(40);
+    }
+    __threadfence_block();
+    return true;
+}
+struct WTk { uint32_t j, slot, base, op_start, valid_lo, safe, aux; int cf, blk; };
+__device__ __forceinline__ WTk read_ticket(WCtl* ctl, uint32_t t)
+{
+    const uint32_t a = smem_u32(&ctl->ticket[t & (kTickets - 1)]);
+    const uint4 x = lds128(a), y = lds128(a + 16u);
+    WTk k; k.j = x.x >> 16; k.slot = x.x & 0xFFFFu; k.cf = (int)x.y; k.op_start = x.z; k.base = x.w;
+    k.valid_lo = y.x; k.blk = (int)y.y; k.safe = y.z; k.aux = y.w;
+    return k;
+}
+
+// stage L: descriptors into shared memory, literals into the ring (tickets w, w + kWL, ...)
+__device__ void wstage_literals(const DecompressArgs& a, int w, WCtl* ctl, uint32_t out_s, uint32_t desc_s, uint32_t stage_s, const uint4* garena)
 {
     constexpr uint32_t M = kWM;
     const uint32_t lane = lane_id();
-    int cached_blk = -1; uint8_t* blk_out = nullptr; const uint8_t* blk_gbase = nullptr;
-    WSTAT_DECL(10)      // 0 waiting for a ticket, 1 loads, 2 literals, 3 phase X waiting, 4 phase X copying, 5 straddle wait, 6 phase I, 7 flush + done, 8 bulk, 9 tickets
-    for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(&ctl->next_ticket, 1u);
-        t = __shfl_sync(kFull, t, 0);
-        const uint32_t k = t & (kTickets - 1);
-        bool fin = false;
-        while (vld(&ctl->tready[k]) != t + 1) { if (vld(&ctl->finished)) { fin = true; break; } __nanosleep(20); }
-        if (fin) break;
-        WSTAT(0) WSTAT_COUNT(9)
-        __threadfence_block();
-        const uint4 tk = lds128(smem_u32(&ctl->ticket[k])), tk2 = lds128(smem_u32(&ctl->ticket[k]) + 16u);
-        const uint32_t valid_lo = tk2.x, fpos_t = tk2.z, lo_h = tk2.w;
-        const int blk = (int)tk2.y;
-        const uint32_t j = tk.x >> 16, slot = tk.x & 0xFFFFu, base = tk.w, op_start = tk.z;
-        const int cf = (int)tk.y;
-
-        const int cnt = cf & 0xFF;
-        const uint32_t nvec_h = ((uint32_t)cf >> 8) & 0xFFu;                 // 16-byte vectors of compressed input the batch's literals lie in (0: not given)
+    int cached_blk = -1; const uint8_t* blk_gbase = nullptr;
+    WSTAT_DECL(4)       // 0 waiting for a ticket, 1 loads, 2 copy, 3 tickets
+    for (uint32_t t = (uint32_t)w;; t += kWL) {
+        if (!wait_ticket(ctl, t)) break;
+        WSTAT(0) WSTAT_COUNT(3)
+        const WTk k = read_ticket(ctl, t);
+        const int cnt = k.cf & 0xFF;
+        uint32_t nvec = ((uint32_t)k.cf >> 8) & 0xFFu, lo = k.aux;       // where the batch's literals lie (0 vectors: not given)
         uint4 d = make_uint4(0, 0, 0, 0);
-        if ((int)lane < cnt) d = ld_cg_128(garena + ((size_t)j * kWR + slot) * 32 + lane);
-        if (blk != cached_blk) {
-            const BlockGeom g = block_geom(a, blk);
-            blk_out = g.out; blk_gbase = g.payload - (reinterpret_cast<uintptr_t>(g.payload) & 15);
-            cached_blk = blk;
+        if ((int)lane < cnt) d = ld_cg_128(garena + ((size_t)k.j * kWR + k.slot) * 32 + lane);
+        if (k.blk != cached_blk && cnt) {
+            const BlockGeom g = block_geom(a, k.blk);
+            blk_gbase = g.payload - (reinterpret_cast<uintptr_t>(g.payload) & 15);
+            cached_blk = k.blk;
         }
-        if (cf & kBulk) {
-            // ---- one piece of a long sequence
+        const uint32_t dslot = desc_s + (t & (kWSlots - 1)) * 512u;
+        if (k.cf & kBulk) {
             const uint32_t lit_src = __shfl_sync(kFull, d.x, 0), lit = __shfl_sync(kFull, d.y, 0);
-            const uint32_t mlen = __shfl_sync(kFull, d.z, 0), dist = __shfl_sync(kFull, d.w, 0);
-            const uint32_t pos = base + op_start;
-            uint8_t* gout = blk_out + op_start;
-            if (lit) {
-                copy_g2r<true>(out_s, pos, blk_gbase + lit_src, lit);
-                __threadfence_block();
-                __syncwarp();
-                bits_set_coop(bits_s, pos, lit);
-                flush_r2g(out_s, gout, pos, lit);
-            }
-            if (mlen) {
-                const uint32_t m_pos = pos + lit, from = m_pos - dist;
-                if ((int)(from - valid_lo) >= 0) {                          // (else: the block is rejected at its end; nothing to wait for)
-                    const uint32_t need_n = mlen < dist ? mlen : dist;
-                    while (!bits_ready_coop(bits_s, from, need_n)) __nanosleep(32);
-                    __threadfence_block();
-                    coop_long_match(out_s, m_pos, mlen, dist);
-                }
-                __threadfence_block();
-                __syncwarp();
-                bits_set_coop(bits_s, m_pos, mlen);
-                flush_r2g(out_s, gout + lit, m_pos, mlen);
-            }
-            WSTAT(8)
+            sts128(dslot + 16u * lane, d.x, d.y, d.z, d.w);
+            if (lit) copy_g2r<true>(out_s, k.base + k.op_start, blk_gbase + lit_src, lit);
         } else if (cnt) {
-            // ---- up to 32 short sequences, one per lane
-            // the batch's compressed bytes: one coalesced 128-bit pass into this warp's staging buffer.  The parser put the
-            // range into the batch header, so these loads are in flight together with the descriptor load above
-            // (a block's last batch carries no range: take it from the descriptors).
-            uint32_t lo = lo_h, nvec = nvec_h;
+            sts128(dslot + 16u * lane, d.x, d.y, d.z, d.w);
+            const uint32_t lit = d.y & 0xFFu;
             if (nvec == 0) {
                 lo = __shfl_sync(kFull, d.x, 0) & ~15u;
-                nvec = (__shfl_sync(kFull, d.x + (d.y & 0xFFu), cnt - 1) - lo + 15u) >> 4;
+                nvec = (__shfl_sync(kFull, d.x + lit, cnt - 1) - lo + 15u) >> 4;
             }
             const bool staged = nvec <= (uint32_t)(kWStage / 16);
             if (staged) {
@@ -594,94 +534,142 @@ __device__ void wcopier_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_s,
                 if (lane + 32u < nvec) sts128(stage_s + 16u * (lane + 32u), x1.x, x1.y, x1.z, x1.w);
                 if (lane + 64u < nvec) sts128(stage_s + 16u * (lane + 64u), x2.x, x2.y, x2.z, x2.w);
             }
-            const bool is_seq = (int)lane < cnt;
-            const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
-            const uint32_t lit_pos = base + d.z, m_pos = lit_pos + lit, from = m_pos - dist;
-            const uint32_t s_pos = __shfl_sync(kFull, lit_pos, 0);
-            const uint32_t e_pos = __shfl_sync(kFull, m_pos + mlen, cnt - 1);
             __syncwarp();
             WSTAT(1)
-            if (is_seq && lit) {
-                if (staged) {
-                    lane_copy4(out_s, lit_pos, stage_s, d.x - lo, 0xFFFFFFFFu, lit);
-                } else {
-                    const uint8_t* gp = blk_gbase + d.x;
-                    for (uint32_t i = 0; i < lit; i++) sts8(out_s + ((lit_pos + i) & M), (uint32_t)__ldg(gp + i));
-                }
+            const uint32_t lit_pos = k.base + d.z;
+            if ((int)lane < cnt && lit) {
+                if (staged) lane_copy4(out_s, lit_pos, stage_s, d.x - lo, 0xFFFFFFFFu, lit);
+                else { const uint8_t* gp = blk_gbase + d.x; for (uint32_t i = 0; i < lit; i++) sts8(out_s + ((lit_pos + i) & M), (uint32_t)__ldg(gp + i)); }
             }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) vst(&ctl->lit_done[t & (kTickets - 1)], t + 1);
+        WSTAT(2)
+    }
+    WSTAT_FLUSH(a, 8, 4)
+}
+
+// stage F: matches whose source is final before the ticket starts, lane-parallel (tickets w, w + kWF, ...)
+__device__ void wstage_far(const DecompressArgs& a, int w, WCtl* ctl, uint32_t out_s, uint32_t desc_s)
+{
+    const uint32_t lane = lane_id();
+    WSTAT_DECL(3)       // 0 waiting (ticket, descriptors), 1 waiting for the serial stage, 2 copy
+    for (uint32_t t = (uint32_t)w;; t += kWF) {
+        if (!wait_ticket(ctl, t)) break;
+        const WTk k = read_ticket(ctl, t);
+        const int cnt = k.cf & 0xFF;
+        if (!(k.cf & kBulk) && cnt) {
+            wait_flag(ctl->lit_done, t);                                    // (the descriptors are in shared memory)
+            WSTAT(0)
+            // everything below `safe` (the start of ticket t - kWDepth) is final once stage N has finished ticket t - kWDepth - 1
+            while ((int)(vld(&ctl->near_next) + (uint32_t)kWDepth - t) < 0) __nanosleep(20);
             __threadfence_block();
-            if (is_seq && lit) bits_set(bits_s, lit_pos, lit);
-            const bool has_match = is_seq && mlen != 0;
-            const uint32_t need_n = mlen < dist ? mlen : dist;
-            const bool doomed = (int)(from - valid_lo) < 0;                 // reads below the dictionary: the block will be rejected
-            // phase X: matches whose source lies wholly before this batch (other warps' output): whichever are ready, lane-parallel
-            const bool external = has_match && (int)(from + need_n - s_pos) <= 0;
-            bool pend = external;
-            WSTAT(2)
-            while (__ballot_sync(kFull, pend)) {
-                // (everything below the completion frontier the ticket was issued at is final: no need to look at its bits)
-                const bool rdy = pend && (doomed || (int)(from + need_n - fpos_t) <= 0 || bits_ready(bits_s, from, need_n));
-                if (__ballot_sync(kFull, rdy)) {
-                    __threadfence_block();
-                    if (rdy && !doomed) {
-                        if (dist >= 4u) lane_copy4(out_s, m_pos, out_s, from, M, mlen);
-                        else for (uint32_t i = 0; i < mlen; i++) sts8(out_s + ((m_pos + i) & M), lds8(out_s + ((from + i) & M)));
-                    }
-                    __threadfence_block();
-                    if (rdy) bits_set(bits_s, m_pos, mlen);
-                    pend = pend && !rdy;
-                    WSTAT(4)
-                } else { __nanosleep(20); WSTAT(3) }
+            WSTAT(1)
+            const uint4 d = lds128(desc_s + (t & (kWSlots - 1)) * 512u + 16u * lane);
+            const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
+            const uint32_t m_pos = k.base + d.z + lit, from = m_pos - dist;
+            const bool far = (int)lane < cnt && mlen != 0 && (int)(from + mlen - k.safe) <= 0 && (int)(from - k.valid_lo) >= 0;
+            if (far) lane_copy4(out_s, m_pos, out_s, from, kWM, mlen);
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) vst(&ctl->far_done[t & (kTickets - 1)], t + 1);
+        WSTAT(2)
+    }
+    WSTAT_FLUSH(a, 12, 3)
+}
+
+// stage N: the serial chain -- near matches in stream order, each copied by all lanes; long match pieces
+__device__ void wstage_near(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, uint32_t desc_s)
+{
+    constexpr uint32_t M = kWM;
+    const uint32_t lane = lane_id();
+    WSTAT_DECL(4)       // 0 waiting for stages L / F, 1 near matches, 2 long matches, 3 near matches (count)
+    for (uint32_t t = 0;; t++) {
+        if (!wait_ticket(ctl, t)) break;
+        const WTk k = read_ticket(ctl, t);
+        const int cnt = k.cf & 0xFF;
+        wait_flag(ctl->lit_done, t);
+        wait_flag(ctl->far_done, t);
+        WSTAT(0)
+        const uint32_t dslot = desc_s + (t & (kWSlots - 1)) * 512u;
+        if (k.cf & kBulk) {
+            const uint4 d = lds128(dslot);
+            const uint32_t lit = d.y, mlen = d.z, dist = d.w;
+            if (mlen) {
+                const uint32_t m_pos = k.base + k.op_start + lit, from = m_pos - dist;
+                if ((int)(from - k.valid_lo) >= 0) coop_long_match(out_s, m_pos, mlen, dist);      // (else: the block is rejected at its end)
             }
-            // phase I: matches that read bytes of this batch, in order, each copied by all lanes (the narrow kernel's phase B).
-            // A source may start up to 64 bytes below the batch: those bytes belong to earlier tickets and must be complete.
-            uint32_t dep = __ballot_sync(kFull, has_match && !external);
+            WSTAT(2)
+        } else if (cnt) {
+            const uint4 d = lds128(dslot + 16u * lane);
+            const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
+            const uint32_t m_pos = k.base + d.z + lit, from = m_pos - dist;
+            const bool has_match = (int)lane < cnt && mlen != 0;
+            const bool doomed = (int)(from - k.valid_lo) < 0;               // reads below the dictionary: the block will be rejected
+            const bool far = (int)(from + mlen - k.safe) <= 0;              // (stage F's test)
+            uint32_t dep = __ballot_sync(kFull, has_match && !far && !doomed);
             if (dep) {
-                const int below = (has_match && !external && !doomed) ? (int)(s_pos - from) : 0;      // > 0: reads that many bytes below the batch
-                const int reach = __reduce_max_sync(kFull, below);
-                if (reach > 0 && (int)(s_pos - fpos_t) > 0) {
-                    while (!bits_ready_coop(bits_s, s_pos - (uint32_t)reach, (uint32_t)reach)) __nanosleep(20);
-                    __threadfence_block();
-                }
-                WSTAT(5)
+                // every lane leaves {destination, length, offset, reciprocal} of its match in its (consumed) descriptor slot, so
+                // the loop reads one broadcast 128-bit word per match; an overlapping match (offset < length <= 64) repeats
+                // its first `offset` bytes: byte i comes from source byte i mod offset, through a 16-bit fixed-point
+                // reciprocal that is exact for i < 64 (0 makes it the identity)
+                const uint32_t inv = (dist < mlen) ? (uint32_t)(65536.0f * __frcp_rn((float)dist)) + 2u : 0u;
                 __syncwarp();
-                const uint32_t par_s = stage_s;                             // (the staged input has been consumed)
-                {
-                    const uint32_t inv = (dist < mlen) ? (uint32_t)(65536.0f * __frcp_rn((float)dist)) + 2u : 0u;
-                    sts128(par_s + 16u * lane, m_pos, doomed ? 0u : mlen, dist, inv);
-                }
+                sts128(dslot + 16u * lane, m_pos, mlen, dist, inv);
                 __syncwarp();
                 const uint32_t i1 = lane + 32;
-                uint4 nx = lds128(par_s + 16u * (uint32_t)(__ffs(dep) - 1));
-                uint32_t rest = dep;
+                uint4 nx = lds128(dslot + 16u * (uint32_t)(__ffs(dep) - 1));
                 for (;;) {
-                    rest &= rest - 1;
+                    dep &= dep - 1;
                     const uint4 cu = nx;
-                    if (rest) nx = lds128(par_s + 16u * (uint32_t)(__ffs(rest) - 1));
+                    if (dep) nx = lds128(dslot + 16u * (uint32_t)(__ffs(dep) - 1));
                     const uint32_t csa = cu.x - cu.z;
                     const uint32_t k0 = lane - ((lane * cu.w) >> 16) * cu.z, k1 = i1 - ((i1 * cu.w) >> 16) * cu.z;
                     if (lane < cu.y) sts8(out_s + ((cu.x + lane) & M), lds8(out_s + ((csa + k0) & M)));
                     if (i1 < cu.y) sts8(out_s + ((cu.x + i1) & M), lds8(out_s + ((csa + k1) & M)));
                     __syncwarp();
-                    if (!rest) break;
+                    WSTAT_COUNT(3)
+                    if (!dep) break;
                 }
-                __threadfence_block();
-                if (has_match && !external) bits_set(bits_s, m_pos, mlen);
-                WSTAT(6)
             }
-            __syncwarp();
-            flush_r2g(out_s, blk_out + (s_pos - base), s_pos, e_pos - s_pos);
+            WSTAT(1)
         }
-        // ---- report completion (retired in order by the dispatcher)
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) vst(&ctl->done[k], t + 1);
-        WSTAT(7)
+        if (lane == 0) vst(&ctl->near_next, t + 1);
     }
-    WSTAT_FLUSH(a, 8, 10)
+    WSTAT_FLUSH(a, 15, 4)
 }
 
-constexpr size_t kWSmem = 128 /* alignment slack */ + kWOut + kWBitWords * 4 + kWP * kWIn + kWP * kWR * 16 + kWC * kWStage + sizeof(WCtl);
+// stage G: finished batches leave for global memory (tickets w, w + kWG, ...)
+__device__ void wstage_flush(const DecompressArgs& a, int w, WCtl* ctl, uint32_t out_s)
+{
+    const uint32_t lane = lane_id();
+    int cached_blk = -1; uint8_t* blk_out = nullptr;
+    WSTAT_DECL(2)       // 0 waiting, 1 flush
+    for (uint32_t t = (uint32_t)w;; t += kWG) {
+        if (!wait_ticket(ctl, t)) break;
+        const WTk k = read_ticket(ctl, t);
+        const uint32_t e = vld(&ctl->tend[t & (kTickets - 1)]);
+        while ((int)(vld(&ctl->near_next) - t) <= 0) __nanosleep(20);
+        __threadfence_block();
+        WSTAT(0)
+        const uint32_t s_pos = k.base + k.op_start;
+        if (e != s_pos) {
+            if (k.blk != cached_blk) { blk_out = a.dst + a.dst_off[k.blk]; cached_blk = k.blk; }
+            flush_r2g(out_s, blk_out + k.op_start, s_pos, e - s_pos);
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) vst(&ctl->done[t & (kTickets - 1)], t + 1);
+        WSTAT(1)
+    }
+    WSTAT_FLUSH(a, 19, 2)
+}
+
+constexpr size_t kWSmem = 128 /* alignment slack */ + kWOut + kWP * kWIn + kWP * kWR * 16 + kWSlots * 512 + kWL * kWStage + sizeof(WCtl);
 
 __global__ void __launch_bounds__(kWThreads, 1)
 decompress_kernel_wide(DecompressArgs a)
@@ -689,25 +677,29 @@ decompress_kernel_wide(DecompressArgs a)
     extern __shared__ __align__(16) uint8_t smem_dyn[];
     uint8_t* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     uint8_t* out_ring = base;
-    uint8_t* bits = out_ring + kWOut;
-    uint8_t* in_rings = bits + kWBitWords * 4;
+    uint8_t* in_rings = out_ring + kWOut;
     uint8_t* hdrs = in_rings + kWP * kWIn;
-    uint8_t* stages = hdrs + kWP * kWR * 16;
-    WCtl* ctl = reinterpret_cast<WCtl*>(stages + kWC * kWStage);
+    uint8_t* descs = hdrs + kWP * kWR * 16;
+    uint8_t* stages = descs + kWSlots * 512;
+    WCtl* ctl = reinterpret_cast<WCtl*>(stages + kWL * kWStage);
     for (uint32_t i = threadIdx.x; i < sizeof(WCtl) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ctl)[i] = 0u;
     __syncthreads();
     const int warp = (int)(threadIdx.x >> 5);
     uint4* garena = a.wide_arena + (size_t)blockIdx.x * (kWideArenaPerCta / 16);
-    uint32_t out_s, bits_s;         // laundered so that the compiler keeps them in registers
+    uint32_t out_s;             // laundered so that the compiler keeps it in a register
     asm volatile("mov.u32 %0, %1;" : "=r"(out_s) : "r"(smem_u32(out_ring)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(bits_s) : "r"(smem_u32(bits)));
-    if (warp < kWP)
-        wparser_main(a, warp, ctl, smem_u32(in_rings) + (uint32_t)warp * kWIn, smem_u32(hdrs) + (uint32_t)warp * kWR * 16u,
-                     garena + (size_t)warp * kWR * 32);
-    else if (warp == kWP)
-        wdispatch_main(a, ctl, out_s, bits_s, smem_u32(hdrs));
-    else
-        wcopier_main(a, ctl, out_s, bits_s, smem_u32(stages) + (uint32_t)(warp - kWP - 1) * kWStage, garena);
+    const uint32_t desc_s = smem_u32(descs);
+    int r = warp;
+    if (r < kWP) { wparser_main(a, r, ctl, smem_u32(in_rings) + (uint32_t)r * kWIn, smem_u32(hdrs) + (uint32_t)r * kWR * 16u, garena + (size_t)r * kWR * 32); return; }
+    r -= kWP;
+    if (r == 0) { wdispatch_main(a, ctl, out_s, smem_u32(hdrs)); return; }
+    r -= 1;
+    if (r < kWL) { wstage_literals(a, r, ctl, out_s, desc_s, smem_u32(stages) + (uint32_t)r * kWStage, garena); return; }
+    r -= kWL;
+    if (r < kWF) { wstage_far(a, r, ctl, out_s, desc_s); return; }
+    r -= kWF;
+    if (r == 0) { wstage_near(a, ctl, out_s, desc_s); return; }
+    wstage_flush(a, r - 1, ctl, out_s);
 }
 
 }  // namespace

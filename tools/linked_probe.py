@@ -67,7 +67,8 @@ def main():
             if args.stats:
                 st = scratch[16:256].cpu().numpy().view(np.uint64)
                 names = ["parser total", "parser ring wait", "batches", "-", "disp other", "disp wait parser", "disp wait flow", "disp open/close",
-                         "cop wait ticket", "cop loads", "cop literals", "cop X wait", "cop X copy", "cop straddle wait", "cop phase I", "cop flush", "cop bulk", "tickets"]
+                         "L wait", "L loads", "L copy", "L tickets", "F wait L", "F wait N", "F copy", "N wait", "N near", "N long", "N near count",
+                         "G wait", "G flush"]
                 print("   stats (Mcycles summed over warps): " + ", ".join(f"{n}={int(v) / 1e6:.1f}" for n, v in zip(names, st)))
             dms = e[0].elapsed_time(e[1])
             ok = bool(torch.equal(d_back[:total], d_src))
