@@ -13,9 +13,9 @@
 //                    64 KiB block: L2-resident) and a 16-byte batch header into a shared-memory ring.
 //   1 DISPATCHER warp hands batches out strictly in stream order as numbered tickets (which parser's ring is next, the
 //                    batch's absolute output position, flow control, in-order retirement, stream begin / end).
-//   10 COPIER warps  in four roles that form a pipeline over the tickets.  The stream's last 128 KiB of output live in a
+//   13 COPIER warps  in four roles that form a pipeline over the tickets.  The stream's last 128 KiB of output live in a
 //                    shared-memory ring indexed by stream position.
-//       L (3 warps)  literals: descriptor batch -> shared memory, the batch's compressed bytes -> staging (one coalesced
+//       L (6 warps)  literals: descriptor batch -> shared memory, the batch's compressed bytes -> staging (one coalesced
 //                    pass, range given by the parser), every lane copies the literals of its sequence into the ring.
 //                    No dependencies at all, so L runs ahead.
 //       F (4 warps)  FAR matches, lane-parallel: a match of ticket t whose source ends below the start of ticket t - 2
@@ -41,7 +41,7 @@ using namespace dec;
 namespace {
 
 constexpr int kWP = kWideParsers;                 // parser warps
-constexpr int kWL = 3, kWF = 4, kWG = 2;           // copier warps per role: literals, far matches, flush (+ one serial warp N)
+constexpr int kWL = 6, kWF = 4, kWG = 2;           // copier warps per role: literals, far matches, flush (+ one serial warp N)
 constexpr int kWC = kWL + kWF + 1 + kWG;
 constexpr int kWThreads = (kWP + 1 + kWC) * 32;   // + the dispatcher warp
 #ifndef B200LZ4_WIDE_DEPTH
@@ -83,6 +83,7 @@ struct WCtl {                                     // shared memory
     uint32_t wr_pub[kWP];                         // parsers: batches published
     uint32_t cons[kWP];                           // dispatcher: batches retired (parsers wait on it for ring space)
     uint32_t tready[kTickets];                    // dispatcher: ticket t issued <=> tready[t % 64] == t + 1
+    uint32_t near_mask[kWSlots], near_long[kWSlots];      // stage F -> N: which sequences of the batch have a near match / the batch is a long match piece
     uint32_t lit_done[kTickets], far_done[kTickets];      // stages L / F: ticket t done <=> flag[t % 64] == t + 1
     uint32_t done[kTickets];                      // stage G: ticket t is in global memory <=> done[t % 64] == t + 1
     uint32_t tend[kTickets], tn[kTickets], tj[kTickets];      // dispatcher-private: end position / ring slot / parser of a ticket
@@ -550,7 +551,11 @@ __device__ void wstage_literals(const DecompressArgs& a, int w, WCtl* ctl, uint3
     WSTAT_FLUSH(a, 8, 4)
 }
 
-// stage F: matches whose source is final before the ticket starts, lane-parallel (tickets w, w + kWF, ...)
+// stage F: matches whose source is final before the ticket starts, lane-parallel (tickets w, w + kWF, ...).  It also
+// prepares the serial stage's work: the parameters {destination, length, offset, reciprocal} of every match replace the
+// (consumed) descriptors, and one word says which of them are NEAR, so that stage N spends nothing on bookkeeping.
+// An overlapping match (offset < length <= 64) repeats its first `offset` bytes: byte i comes from source byte i mod
+// offset, through a 16-bit fixed-point reciprocal that is exact for i < 64 (0 makes it the identity).
 __device__ void wstage_far(const DecompressArgs& a, int w, WCtl* ctl, uint32_t out_s, uint32_t desc_s)
 {
     const uint32_t lane = lane_id();
@@ -559,22 +564,46 @@ __device__ void wstage_far(const DecompressArgs& a, int w, WCtl* ctl, uint32_t o
         if (!wait_ticket(ctl, t)) break;
         const WTk k = read_ticket(ctl, t);
         const int cnt = k.cf & 0xFF;
-        if (!(k.cf & kBulk) && cnt) {
+        const uint32_t dslot = desc_s + (t & (kWSlots - 1)) * 512u;
+        uint32_t nmask = 0, nlong = 0;
+        if (cnt) {
             wait_flag(ctl->lit_done, t);                                    // (the descriptors are in shared memory)
             WSTAT(0)
-            // everything below `safe` (the start of ticket t - kWDepth) is final once stage N has finished ticket t - kWDepth - 1
-            while ((int)(vld(&ctl->near_next) + (uint32_t)kWDepth - t) < 0) __nanosleep(20);
-            __threadfence_block();
-            WSTAT(1)
-            const uint4 d = lds128(desc_s + (t & (kWSlots - 1)) * 512u + 16u * lane);
-            const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
-            const uint32_t m_pos = k.base + d.z + lit, from = m_pos - dist;
-            const bool far = (int)lane < cnt && mlen != 0 && (int)(from + mlen - k.safe) <= 0 && (int)(from - k.valid_lo) >= 0;
-            if (far) lane_copy4(out_s, m_pos, out_s, from, kWM, mlen);
+            const uint4 d = lds128(dslot + 16u * lane);
+            if (k.cf & kBulk) {
+                const uint32_t lit = __shfl_sync(kFull, d.y, 0), mlen = __shfl_sync(kFull, d.z, 0), dist = __shfl_sync(kFull, d.w, 0);
+                const uint32_t m_pos = k.base + k.op_start + lit;
+                if (mlen && (int)(m_pos - dist - k.valid_lo) >= 0) {        // (else: the block is rejected at its end)
+                    nlong = 1;
+                    __syncwarp();
+                    if (lane == 0) sts128(dslot, m_pos, mlen, dist, 0u);
+                }
+            } else {
+                const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
+                const uint32_t m_pos = k.base + d.z + lit, from = m_pos - dist;
+                const bool live = (int)lane < cnt && mlen != 0 && (int)(from - k.valid_lo) >= 0;     // (a match below the dictionary: block rejected)
+                const bool far = live && (int)(from + mlen - k.safe) <= 0;
+                nmask = __ballot_sync(kFull, live && !far);
+                if (nmask) {
+                    const uint32_t inv = (dist < mlen) ? (uint32_t)(65536.0f * __frcp_rn((float)dist)) + 2u : 0u;
+                    sts128(dslot + 16u * lane, m_pos, mlen, dist, inv);     // (every lane has read its own descriptor)
+                }
+                // everything below `safe` (the start of ticket t - kWDepth) is final once stage N has finished ticket t - kWDepth - 1
+                if (__ballot_sync(kFull, far)) {
+                    while ((int)(vld(&ctl->near_next) + (uint32_t)kWDepth - t) < 0) __nanosleep(20);
+                    __threadfence_block();
+                    WSTAT(1)
+                    if (far) lane_copy4(out_s, m_pos, out_s, from, kWM, mlen);
+                }
+            }
         }
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) vst(&ctl->far_done[t & (kTickets - 1)], t + 1);
+        if (lane == 0) {
+            vst(&ctl->near_mask[t & (kWSlots - 1)], nmask); vst(&ctl->near_long[t & (kWSlots - 1)], nlong);
+            __threadfence_block();
+            vst(&ctl->far_done[t & (kTickets - 1)], t + 1);
+        }
         WSTAT(2)
     }
     WSTAT_FLUSH(a, 12, 3)
@@ -585,54 +614,37 @@ __device__ void wstage_near(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, 
 {
     constexpr uint32_t M = kWM;
     const uint32_t lane = lane_id();
-    WSTAT_DECL(4)       // 0 waiting for stages L / F, 1 near matches, 2 long matches, 3 near matches (count)
+    const uint32_t i1 = lane + 32;
+    WSTAT_DECL(4)       // 0 waiting for stage F, 1 near matches, 2 long matches, 3 near matches (count)
     for (uint32_t t = 0;; t++) {
-        if (!wait_ticket(ctl, t)) break;
-        const WTk k = read_ticket(ctl, t);
-        const int cnt = k.cf & 0xFF;
-        wait_flag(ctl->lit_done, t);
-        wait_flag(ctl->far_done, t);
-        WSTAT(0)
+        bool fin = false;
+        while (vld(&ctl->far_done[t & (kTickets - 1)]) != t + 1) {          // (stage F has waited for the ticket and for stage L)
+            if (vld(&ctl->finished) && (int)(t - vld(&ctl->t_final)) >= 0) { fin = true; break; }
+            __nanosleep(20);
+        }
+        if (fin) break;
+        __threadfence_block();
+        uint32_t dep = vld(&ctl->near_mask[t & (kWSlots - 1)]);
+        const uint32_t is_long = vld(&ctl->near_long[t & (kWSlots - 1)]);
         const uint32_t dslot = desc_s + (t & (kWSlots - 1)) * 512u;
-        if (k.cf & kBulk) {
+        WSTAT(0)
+        if (is_long) {
             const uint4 d = lds128(dslot);
-            const uint32_t lit = d.y, mlen = d.z, dist = d.w;
-            if (mlen) {
-                const uint32_t m_pos = k.base + k.op_start + lit, from = m_pos - dist;
-                if ((int)(from - k.valid_lo) >= 0) coop_long_match(out_s, m_pos, mlen, dist);      // (else: the block is rejected at its end)
-            }
+            coop_long_match(out_s, d.x, d.y, d.z);
             WSTAT(2)
-        } else if (cnt) {
-            const uint4 d = lds128(dslot + 16u * lane);
-            const uint32_t lit = d.y & 0xFFu, mlen = (d.y >> 8) & 0xFFu, dist = d.y >> 16;
-            const uint32_t m_pos = k.base + d.z + lit, from = m_pos - dist;
-            const bool has_match = (int)lane < cnt && mlen != 0;
-            const bool doomed = (int)(from - k.valid_lo) < 0;               // reads below the dictionary: the block will be rejected
-            const bool far = (int)(from + mlen - k.safe) <= 0;              // (stage F's test)
-            uint32_t dep = __ballot_sync(kFull, has_match && !far && !doomed);
-            if (dep) {
-                // every lane leaves {destination, length, offset, reciprocal} of its match in its (consumed) descriptor slot, so
-                // the loop reads one broadcast 128-bit word per match; an overlapping match (offset < length <= 64) repeats
-                // its first `offset` bytes: byte i comes from source byte i mod offset, through a 16-bit fixed-point
-                // reciprocal that is exact for i < 64 (0 makes it the identity)
-                const uint32_t inv = (dist < mlen) ? (uint32_t)(65536.0f * __frcp_rn((float)dist)) + 2u : 0u;
+        } else if (dep) {
+            uint4 nx = lds128(dslot + 16u * (uint32_t)(__ffs(dep) - 1));
+            for (;;) {
+                dep &= dep - 1;
+                const uint4 cu = nx;
+                if (dep) nx = lds128(dslot + 16u * (uint32_t)(__ffs(dep) - 1));
+                const uint32_t csa = cu.x - cu.z;
+                const uint32_t k0 = lane - ((lane * cu.w) >> 16) * cu.z, k1 = i1 - ((i1 * cu.w) >> 16) * cu.z;
+                if (lane < cu.y) sts8(out_s + ((cu.x + lane) & M), lds8(out_s + ((csa + k0) & M)));
+                if (i1 < cu.y) sts8(out_s + ((cu.x + i1) & M), lds8(out_s + ((csa + k1) & M)));
                 __syncwarp();
-                sts128(dslot + 16u * lane, m_pos, mlen, dist, inv);
-                __syncwarp();
-                const uint32_t i1 = lane + 32;
-                uint4 nx = lds128(dslot + 16u * (uint32_t)(__ffs(dep) - 1));
-                for (;;) {
-                    dep &= dep - 1;
-                    const uint4 cu = nx;
-                    if (dep) nx = lds128(dslot + 16u * (uint32_t)(__ffs(dep) - 1));
-                    const uint32_t csa = cu.x - cu.z;
-                    const uint32_t k0 = lane - ((lane * cu.w) >> 16) * cu.z, k1 = i1 - ((i1 * cu.w) >> 16) * cu.z;
-                    if (lane < cu.y) sts8(out_s + ((cu.x + lane) & M), lds8(out_s + ((csa + k0) & M)));
-                    if (i1 < cu.y) sts8(out_s + ((cu.x + i1) & M), lds8(out_s + ((csa + k1) & M)));
-                    __syncwarp();
-                    WSTAT_COUNT(3)
-                    if (!dep) break;
-                }
+                WSTAT_COUNT(3)
+                if (!dep) break;
             }
             WSTAT(1)
         }
