@@ -476,7 +476,7 @@ cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream)
     b.debug = dbg ? atoi(dbg) : 0;
     // Wide kernel (one stream per SM, parallel block parsers + out-of-order copiers): linked streams when there are
     // few enough of them that the narrow kernel would leave most of the GPU idle; few independent blocks likewise.
-    bool wide = a.stream_first ? (a.n_streams <= 4 * sm_count) : (a.n_streams <= sm_count);
+    bool wide = a.stream_first ? (a.n_streams <= 2 * sm_count) : (a.n_streams <= sm_count);
     if (wide_env) wide = wide_env[0] == '1';
     if (wide && a.wide_arena) return launch_decompress_wide(b, sm_count, stream);
     const int max_ctas = sm_count * 16;
