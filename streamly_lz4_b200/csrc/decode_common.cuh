@@ -147,21 +147,25 @@ __device__ int parse_block(PT& P, int skew, int src_len, int cap, uint32_t dict_
     for (;;) {
         if (P.fill + kWindowSeqs > kQDepth) P.publish(0, 0, ip);
         if (P.issued_end - ip < 1024) P.top_up(ip);
-        if (ip + 64 > P.ready_end) P.ensure(ip, ip + 64);
-        if (ip + 56 <= iend && op + 1024 <= cap) {
+        if (ip + 72 > P.ready_end) P.ensure(ip, ip + 72);
+        if (ip + 80 <= iend && op + 1024 <= cap) {
             // ---- window path
             const int p = ip + (int)lane;
             const uint32_t tok = lds8(ring_s + ((uint32_t)p & kRM));
-            const uint32_t lit = tok >> 4, ml = tok & 15u;
-            const uint32_t o = (uint32_t)p + 1u + lit;                 // offset field, if lit < 15
+            const uint32_t e1 = lds8(ring_s + (((uint32_t)p + 1u) & kRM));   // the byte after the token (issued with it): a literal-length byte if the nibble is 15
+            const uint32_t ml = tok & 15u;
+            const bool lext = (tok >> 4) == 15u;                       // one literal-length byte, e1 <= 17: 15 .. 32 literals (:1977-1983)
+            const uint32_t lit = lext ? 15u + e1 : (tok >> 4);
+            const uint32_t lsrc = (uint32_t)p + 1u + (lext ? 1u : 0u);  // first literal
+            const uint32_t o = lsrc + (lit <= kShortLit ? lit : 0u);   // offset field
             const uint32_t b0 = lds8(ring_s + (o & kRM));
             const uint32_t b1 = lds8(ring_s + ((o + 1) & kRM));
             const uint32_t b2 = lds8(ring_s + ((o + 2) & kRM));
             const uint32_t dist = b0 | (b1 << 8);                      // :2055
             const bool ext = ml == 15u;
             const uint32_t mlen = ext ? 19u + b2 : ml + 4u;            // one length byte b2 != 255, :2062-2067
-            const uint32_t nxt = lane + 3u + lit + (ext ? 1u : 0u);    // next token, relative to ip
-            const bool simple = lit < 15u && !(ext && b2 == 255u) && mlen <= kShortMatch;
+            const uint32_t nxt = (o - (uint32_t)ip) + 2u + (ext ? 1u : 0u);    // next token, relative to ip
+            const bool simple = lit <= kShortLit && !(ext && b2 == 255u) && mlen <= kShortMatch;
             const uint32_t packed = nxt | ((lit + mlen) << 8) | (simple ? 0u : 0x80000000u);
             uint32_t cur = 0, real = 0;
             int opr = op, my_op = 0;
@@ -184,7 +188,7 @@ __device__ int parse_block(PT& P, int skew, int src_len, int cap, uint32_t dict_
                     P.note_reach(__reduce_max_sync(kFull, reach));
                 }
                 const uint32_t rank = __popc(real & lanemask_lt());
-                if (mine) P.put(rank, (uint32_t)p + 1u, lit | (mlen << 8) | (dist << 16), (uint32_t)my_op, 0u);
+                if (mine) P.put(rank, lsrc, lit | (mlen << 8) | (dist << 16), (uint32_t)my_op, 0u);
                 P.advance(__popc(real), opr);
                 op = opr; ip += (int)cur;
                 continue;
