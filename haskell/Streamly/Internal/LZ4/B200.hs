@@ -14,13 +14,18 @@
 -- STATUS: written against streamly-0.8's internal Array / StreamD API exactly
 -- as the reference uses it, but NOT type-checked in this repository's build
 -- image (no GHC there).  Every behaviour it relies on is exercised at the C
--- ABI by tests/test_gpu_parity.py through streamly_lz4_b200/api.py, which is
--- the same logic in Python.  Drop this file next to
--- src/Streamly/Internal/LZ4.hs and re-export from there (INTEGRATION.md 2).
+-- ABI: examples/ffi_replay.c makes exactly the call sequences below (same
+-- argument marshalling: Int64 offsets, Int32 lengths, 16-byte staged gaps,
+-- @[0, n]@ stream table or NULL for independent blocks) and runs in the GPU test
+-- suite; tests/test_gpu_parity.py does the same through streamly_lz4_b200/api.py.
+-- Drop this file next to src/Streamly/Internal/LZ4.hs, apply
+-- haskell/patches/Config.hs.patch (it implements 'setBlockIndependence') and
+-- re-export from there (INTEGRATION.md 2).
 --
 module Streamly.Internal.LZ4.B200
     ( compressChunksD
     , decompressChunksRawD
+    , resizeChunksD
     , B200Config (..)
     , defaultB200Config
     )
@@ -72,8 +77,22 @@ foreign import ccall safe "b200lz4.h b200lz4_host_alloc"
 foreign import ccall safe "b200lz4.h b200lz4_host_free"
     c_hostFree :: Ptr Word8 -> IO ()
 
+-- The error text is kept in the ctx, not in thread-local storage: an unbound Haskell thread may run the @safe@ batch call
+-- and this call on different OS threads.
+foreign import ccall unsafe "b200lz4.h b200lz4_ctx_last_error"
+    c_ctxLastError :: Ptr C_Ctx -> IO CString
+
 foreign import ccall unsafe "b200lz4.h b200lz4_last_error"
     c_lastError :: IO CString
+
+-- parallel gather of the batch's arrays into the page-locked source buffer (host threads inside the library)
+foreign import ccall safe "b200lz4.h b200lz4_gather_host"
+    c_gatherHost :: Ptr Word8 -> Ptr (Ptr Word8) -> Ptr Int64 -> Ptr Int32 -> CInt -> CInt -> IO CInt
+
+-- resizeChunksD's header walk over one contiguous range
+foreign import ccall unsafe "b200lz4.h b200lz4_reframe"
+    c_reframe :: Ptr Word8 -> Int64 -> CInt -> CInt -> Ptr Int64 -> Ptr Int32 -> Int64
+              -> Ptr Int64 -> Ptr Int64 -> Ptr CInt -> IO CInt
 
 foreign import ccall safe "b200lz4.h b200lz4_cstream_create"
     c_cstreamCreate :: Ptr C_Ctx -> Ptr (Ptr C_CStream) -> IO CInt
@@ -131,6 +150,9 @@ data Session = Session
 lastError :: IO String
 lastError = c_lastError >>= peekCString
 
+ctxError :: Session -> IO String
+ctxError s = c_ctxLastError (sCtx s) >>= peekCString
+
 newSession :: B200Config -> IO Session
 newSession conf = alloca $ \pp -> do
     rc <- c_ctxCreate (fromIntegral (device conf)) pp
@@ -170,16 +192,26 @@ align16 n = (n + 15) `div` 16 * 16
 
 -- | Copy the arrays into the pinned source buffer at 16-byte aligned offsets
 -- with a 16-byte gap (separate Haskell arrays are never adjacent) and return
--- (offsets, lengths).
+-- (offsets, lengths).  The copy itself runs on the library's host threads
+-- (b200lz4_gather_host); the arrays are pinned (streamly allocates them so),
+-- so their addresses stay valid for the duration of the call.
 stage :: Session -> [Array.Array Word8] -> IO ([Int64], [Int32])
-stage s arrs = go 0 arrs [] []
+stage s arrs = do
+    let lens = map Array.byteLength arrs
+        offs = scanl (\at n -> at + align16 (n + 16)) 0 lens
+        n = length arrs
+    withPtrs arrs [] $ \ptrs ->
+      allocaArray n $ \pPtr -> allocaArray n $ \pOff -> allocaArray n $ \pLen -> do
+        pokeArray pPtr ptrs
+        pokeArray pOff (map fromIntegral (take n offs))
+        pokeArray pLen (map fromIntegral lens)
+        rc <- c_gatherHost (sSrc s) pPtr pOff pLen (fromIntegral n) 0
+        when (rc /= 0) $ lastError >>= \e -> error ("b200lz4_gather_host failed: " ++ e)
+    return (map fromIntegral (take n offs), map fromIntegral lens)
   where
-    go _ [] offs lens = return (reverse offs, reverse lens)
-    go at (a:as) offs lens = do
-        let n = Array.byteLength a
-        Array.asPtrUnsafe (Array.unsafeCast a) $ \p ->
-            copyBytes (sSrc s `plusPtr` at) (p :: Ptr Word8) n
-        go (at + align16 (n + 16)) as (fromIntegral at : offs) (fromIntegral n : lens)
+    withPtrs [] acc k = k (reverse acc)
+    withPtrs (a:as) acc k =
+        Array.asPtrUnsafe (Array.unsafeCast a) $ \p -> withPtrs as ((p :: Ptr Word8) : acc) k
 
 -- | Slice a fresh, exactly sized array out of the pinned destination buffer.
 sliceOut :: Ptr Word8 -> Int -> Int -> IO (Array.Array Word8)
@@ -237,7 +269,7 @@ compressBatch cfg speed s0 strm arrs = do
         rc <- c_compressBatch (sCtx s) (sSrc s) srcBytes pOff pLen (fromIntegral n)
                   pF nS pS (fromIntegral speed) (fromIntegral meta)
                   (sDst s) (fromIntegral (sDstCap s)) pDstOff pOutLen
-        when (rc /= 0) $ lastError >>= \e ->
+        when (rc /= 0) $ ctxError s >>= \e ->
             error ("compressChunk: c_compressFastContinue failed. " ++ e)
         dstOff <- peekArray (n + 1) pDstOff
         outs <- forM (zip dstOff (tail dstOff)) $ \(a, b) ->
@@ -276,7 +308,7 @@ decompressBatch cfg s0 strm arrs = do
         rc <- c_decompressBatch (sCtx s) (sSrc s) srcBytes pOff pLen (fromIntegral n)
                   pF nS pS (fromIntegral meta) (fromIntegral maxBlock)
                   (sDst s) (fromIntegral (sDstCap s)) pDstOff pOutLen
-        when (rc /= 0) $ lastError >>= \e ->
+        when (rc /= 0) $ ctxError s >>= \e ->
             error ("decompressChunk: c_decompressSafeContinue failed. " ++ e)
         dstOff <- peekArray n pDstOff
         outLen <- peekArray n pOutLen
@@ -338,8 +370,11 @@ batchedD conf acquire release run (Stream.Stream step0 state0) =
 
 -- | Drop-in for 'Streamly.Internal.LZ4.compressChunksD' (:353-394).  Linked
 -- blocks by default (one device-resident stream state per Haskell stream);
--- independent blocks would pass 'nullPtr' as the stream (the reference's
--- 'setBlockIndependence' is still a stub, Config.hs:142-146).
+-- with @setBlockIndependence True@ (implemented by
+-- haskell/patches/Config.hs.patch; a stub in the reference, Config.hs:142-146)
+-- every array is compressed with a fresh state: no stream handle is created and
+-- the batch call gets a NULL stream table, which is the mode in which all blocks
+-- of a batch run in parallel.
 {-# INLINE_NORMAL compressChunksD #-}
 compressChunksD ::
        MonadIO m
@@ -356,12 +391,14 @@ compressChunksD conf cfg speed0 =
     speed = max speed0 0                                        -- :364
     acquire = do
         s <- newSession conf
-        strm <- alloca $ \pp -> do
-            rc <- c_cstreamCreate (sCtx s) pp
-            when (rc /= 0) $ lastError >>= \e -> error ("b200lz4_cstream_create failed: " ++ e)
-            peek pp
+        strm <- if blockIndependent cfg
+            then return nullPtr
+            else alloca $ \pp -> do
+                rc <- c_cstreamCreate (sCtx s) pp
+                when (rc /= 0) $ lastError >>= \e -> error ("b200lz4_cstream_create failed: " ++ e)
+                peek pp
         return (s, strm)
-    release (s, strm) = c_cstreamFree strm >> freeSession s      -- :393-394
+    release (s, strm) = when (strm /= nullPtr) (c_cstreamFree strm) >> freeSession s      -- :393-394
     run (s, strm) arrs = do
         (s1, outs) <- compressBatch cfg speed s strm arrs
         return ((s1, strm), outs)
@@ -382,12 +419,97 @@ decompressChunksRawD conf cfg =
 
     acquire = do
         s <- newSession conf
-        strm <- alloca $ \pp -> do
-            rc <- c_dstreamCreate (sCtx s) pp
-            when (rc /= 0) $ lastError >>= \e -> error ("b200lz4_dstream_create failed: " ++ e)
-            peek pp
+        strm <- if blockIndependent cfg
+            then return nullPtr
+            else alloca $ \pp -> do
+                rc <- c_dstreamCreate (sCtx s) pp
+                when (rc /= 0) $ lastError >>= \e -> error ("b200lz4_dstream_create failed: " ++ e)
+                peek pp
         return (s, strm)
-    release (s, strm) = c_dstreamFree strm >> freeSession s
+    release (s, strm) = when (strm /= nullPtr) (c_dstreamFree strm) >> freeSession s
     run (s, strm) arrs = do
         (s1, outs) <- decompressBatch cfg s strm arrs
         return ((s1, strm), outs)
+
+--------------------------------------------------------------------------------
+-- Re-framing
+--------------------------------------------------------------------------------
+
+{-# ANN type ResizeState Fuse #-}
+data ResizeState st
+    = RInit st
+    | RHave st (Array.Array Word8)                 -- unconsumed bytes
+    | RYield st (Array.Array Word8) [Array.Array Word8] Bool   -- rest, ready blocks, end mark seen
+    | RDone
+
+-- | Drop-in for 'Streamly.Internal.LZ4.resizeChunksD' (:432-523): the header
+-- walk of one accumulated range is one call of b200lz4_reframe (which consumes
+-- as many complete [header][block] arrays as the range holds and reports the
+-- end mark); the state machine around it -- accumulate while a block is
+-- incomplete, stop at the end mark, "Incomplete block" / "No end mark found"
+-- at the end of the input -- is the reference's.
+{-# INLINE_NORMAL resizeChunksD #-}
+resizeChunksD ::
+       MonadIO m
+    => BlockConfig
+    -> FrameConfig
+    -> Stream.Stream m (Array.Array Word8)
+    -> Stream.Stream m (Array.Array Word8)
+resizeChunksD cfg frameCfg (Stream.Stream step0 state0) =
+    Stream.Stream step (RInit state0)
+
+    where
+
+    meta = metaSize cfg
+    endMark = hasEndMark frameCfg
+    maxBlocks = 4096 :: Int
+
+    -- all complete blocks at the front of `arr`: (blocks, rest, end mark seen)
+    walk arr = liftIO $ do
+        let len = Array.byteLength arr
+        Array.asPtrUnsafe (Array.unsafeCast arr) $ \p ->
+          allocaArray maxBlocks $ \pOff -> allocaArray maxBlocks $ \pLen ->
+          alloca $ \pN -> alloca $ \pUsed -> alloca $ \pEnd -> do
+            rc <- c_reframe (p :: Ptr Word8) (fromIntegral len) (fromIntegral meta)
+                      (if endMark then 1 else 0) pOff pLen (fromIntegral maxBlocks) pN pUsed pEnd
+            when (rc /= 0) $ lastError >>= \e -> error ("resizeChunksD: " ++ e)
+            n <- fromIntegral <$> peek pN
+            used <- fromIntegral <$> peek pUsed
+            ended <- peek pEnd
+            offs <- peekArray n pOff
+            lens <- peekArray n pLen
+            let blocks = [ Array.getSliceUnsafe (fromIntegral o) (fromIntegral l) arr | (o, l) <- zip offs lens ]
+                rest = Array.getSliceUnsafe used (len - used) arr
+            return (blocks, rest, ended /= 0)
+
+    {-# INLINE_LATE step #-}
+    step gst (RInit st) = do
+        r <- step0 gst st
+        case r of
+            Stream.Yield arr st1 -> return $ Stream.Skip $ RHave st1 arr
+            Stream.Skip st1 -> return $ Stream.Skip $ RInit st1
+            Stream.Stop ->
+                if endMark
+                then error "resizeChunksD: No end mark found"          -- :493-496
+                else return Stream.Stop
+    step gst (RHave st arr) = do
+        (blocks, rest, ended) <- walk arr
+        if null blocks && not ended
+        then do                                                      -- RAccumulate, :498-505
+            r <- step0 gst st
+            case r of
+                Stream.Yield more st1 -> do
+                    arr1 <- liftIO $ Array.spliceTwo arr more
+                    return $ Stream.Skip $ RHave st1 arr1
+                Stream.Skip st1 -> return $ Stream.Skip $ RHave st1 arr
+                Stream.Stop ->
+                    if Array.byteLength arr == 0 && not endMark
+                    then return Stream.Stop
+                    else error "resizeChunksD: Incomplete block"     -- :505
+        else return $ Stream.Skip $ RYield st rest blocks ended
+    step _ (RYield st rest (b : bs) ended) = return $ Stream.Yield b (RYield st rest bs ended)
+    step _ (RYield st rest [] ended)
+        | ended = return $ Stream.Skip RDone                         -- RFooter, :506-522: the stream stops at the end mark
+        | Array.byteLength rest == 0 = return $ Stream.Skip $ RInit st
+        | otherwise = return $ Stream.Skip $ RHave st rest
+    step _ RDone = return Stream.Stop

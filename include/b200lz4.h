@@ -264,6 +264,18 @@ int b200lz4_reframe_dev(const void* d_buf, int64_t len, int header_mode, int has
                         int64_t* d_block_off, int32_t* d_block_len, int64_t max_blocks,
                         int64_t* d_result, void* cuda_stream);
 
+/* ------------------------------------------------------------ checksums -- */
+/*
+ * XXH32 (seed as given) of n byte ranges buf[off[i] .. off[i]+len[i]): what the LZ4 frame format uses for its header
+ * checksum byte ((xxh32(descriptor) >> 8) & 0xFF), block checksums and content checksum.  The reference parses the
+ * header checksum with `satisfy (const True)` and rejects both checksum flags (src/Streamly/Internal/LZ4.hs:602,
+ * :631-640); these entry points are what a complete frame reader / writer needs.
+ * _dev: device pointers, enqueue only.  _batch: host pointers (copied to the device, hashed there, results copied back).
+ */
+int b200lz4_xxh32_dev(const void* d_buf, const int64_t* d_off, const int32_t* d_len, int n, uint32_t seed, uint32_t* d_out, void* cuda_stream);
+int b200lz4_xxh32_batch(b200lz4_ctx* ctx, const void* src, int64_t src_bytes, const int64_t* off, const int32_t* len, int n,
+                        uint32_t seed, uint32_t* out);
+
 /* ------------------------------------------------------ legacy aliases -- */
 /* Same names, signatures and return conventions as the 7 symbols the unmodified reference
  * imports (src/Streamly/Internal/LZ4.hs:105-140; cbits/lz4.h:170,182,273-274,336,358-359,409).

@@ -336,3 +336,38 @@ int ora_decompress_continue(ora_dstream* s, const uint8_t* src, uint8_t* dst, in
     s->prev_out = dst; s->prev_len = (size_t)r;
     return r;
 }
+
+
+/* ---------------------------------------------------------------------------
+ * XXH32, restated from its published definition (xxHash is bundled with lz4's
+ * frame library, lib/xxhash.c, which is NOT part of the reference tree: the
+ * reference's frame parser stops at a stub, src/Streamly/Internal/LZ4.hs:602).
+ * Pinned by the known answers in tests/test_oracle.py (empty input, "a", "abc",
+ * a 39-byte sentence, and the frame descriptors 64 40 -> A7, 64 70 -> B9).
+ */
+static inline uint32_t xrotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+uint32_t ora_xxh32(const uint8_t* p, size_t len, uint32_t seed)
+{
+    const uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+    const uint8_t* const end = p + len;
+    uint32_t h;
+    if (len >= 16) {
+        uint32_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+        const uint8_t* const limit = end - 16;
+        do {
+            v1 = xrotl(v1 + rd32(p) * P2, 13) * P1;
+            v2 = xrotl(v2 + rd32(p + 4) * P2, 13) * P1;
+            v3 = xrotl(v3 + rd32(p + 8) * P2, 13) * P1;
+            v4 = xrotl(v4 + rd32(p + 12) * P2, 13) * P1;
+            p += 16;
+        } while (p <= limit);
+        h = xrotl(v1, 1) + xrotl(v2, 7) + xrotl(v3, 12) + xrotl(v4, 18);
+    } else {
+        h = seed + P5;
+    }
+    h += (uint32_t)len;
+    while (p + 4 <= end) { h = xrotl(h + rd32(p) * P3, 17) * P4; p += 4; }
+    while (p < end) { h = xrotl(h + (*p) * P5, 11) * P1; p++; }
+    h ^= h >> 15; h *= P2; h ^= h >> 13; h *= P3; h ^= h >> 16;
+    return h;
+}

@@ -132,6 +132,16 @@ class Context:
     def last_error(self) -> str:
         return self.lib.b200lz4_ctx_last_error(self.handle).decode("utf-8", "replace")
 
+    def xxh32(self, buf: np.ndarray, offs: np.ndarray, lens: np.ndarray, seed: int = 0) -> np.ndarray:
+        """XXH32 of n byte ranges of `buf`, computed on the device (b200lz4_xxh32_batch)."""
+        offs = np.ascontiguousarray(offs, dtype=np.int64); lens = np.ascontiguousarray(lens, dtype=np.int32)
+        out = np.zeros(len(lens), dtype=np.uint32)
+        rc = self.lib.b200lz4_xxh32_batch(self.handle, buf.ctypes.data, buf.size, offs.ctypes.data, lens.ctypes.data, len(lens), seed,
+                                          out.ctypes.data)
+        if rc != 0:
+            raise LZ4Error("b200lz4_xxh32_batch: " + _lib.last_error())
+        return out
+
     def copy_probe(self, h_src: np.ndarray, h2d_bytes: int, h_dst: np.ndarray, d2h_bytes: int, check: bool = False) -> int:
         """One plain H2D + D2H copy pair on the ctx's copy streams (measurement aid, no kernels)."""
         rc = self.lib.b200lz4_copy_probe(self.handle, h_src.ctypes.data, h2d_bytes, h_dst.ctypes.data, d2h_bytes)
@@ -507,10 +517,39 @@ def decompress_chunks(cfg: BlockConfig, chunks: Iterable, *, ctx: Optional[Conte
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# LZ4 frame header, as far as the reference goes (Internal/LZ4.hs:569-651)
+# LZ4 frame format.  First the reference's own stub (Internal/LZ4.hs:569-651), mirrored as
+# it is; then the complete reader / writer the stub stands in for (header checksum, content size, block independence,
+# XXH32 block and content checksums, stored blocks), which is what interoperates with the stock `lz4` tool.
 
 FRAME_MAGIC = 407708164                       # 0x184D2204, little endian on the stream (Internal/LZ4.hs:610)
 _BD_CODES = {4: BlockSize.BlockMax64KB, 5: BlockSize.BlockMax256KB, 6: BlockSize.BlockMax1MB, 7: BlockSize.BlockMax4MB}
+
+
+def _xxh32_short(data: bytes, seed: int = 0) -> int:
+    """XXH32 of fewer than 16 bytes (the frame descriptor is 2 .. 14 bytes): only the tail rounds and the avalanche of the
+    published definition apply.  Payload checksums are computed on the device (Context.xxh32)."""
+    assert len(data) < 16
+    m = 0xFFFFFFFF
+    rotl = lambda x, r: ((x << r) | (x >> (32 - r))) & m
+    h = (seed + 374761393 + len(data)) & m
+    at = 0
+    while at + 4 <= len(data):
+        h = (rotl((h + int.from_bytes(data[at:at + 4], "little") * 3266489917) & m, 17) * 668265263) & m
+        at += 4
+    for b in data[at:]:
+        h = (rotl((h + b * 374761393) & m, 11) * 2654435761) & m
+    h ^= h >> 15; h = (h * 2246822519) & m
+    h ^= h >> 13; h = (h * 3266489917) & m
+    return h ^ (h >> 16)
+
+
+@dataclass(frozen=True)
+class FrameInfo:
+    """What a complete frame descriptor says beyond BlockConfig / FrameConfig."""
+    block_checksum: bool = False
+    content_checksum: bool = False
+    content_size: Optional[int] = None
+    header_len: int = 7
 
 
 def simple_frame_parser(header: bytes, *, allow_independent: bool = False):
@@ -542,10 +581,45 @@ def simple_frame_parser(header: bytes, *, allow_independent: bool = False):
     return BlockConfig(block_size=bs, independent=independent), FrameConfig(has_end_mark=True)   # header checksum: any byte, :602
 
 
-def frame_header(block_size: BlockSize, *, independent: bool = False) -> bytes:
-    """The 7 bytes benchmark/Main.hs:92-100 writes in front of a framed stream (FLG = version 01, BD = block maximum, HC = 0)."""
+def frame_header(block_size: BlockSize, *, independent: bool = False, block_checksum: bool = False,
+                 content_size: Optional[int] = None, content_checksum: bool = False, checksum: bool = True) -> bytes:
+    """A frame header [magic][FLG][BD][content size?][HC].  checksum=False writes HC = 0 like benchmark/Main.hs:92-100
+    (which only the reference's own stub parser accepts); the default is the real (XXH32(descriptor) >> 8) & 0xFF."""
     code = {v: k for k, v in _BD_CODES.items()}[block_size]
-    return FRAME_MAGIC.to_bytes(4, "little") + bytes([0x40 | (0x20 if independent else 0), code << 4, 0])
+    flg = 0x40 | (0x20 if independent else 0) | (0x10 if block_checksum else 0) | (0x08 if content_size is not None else 0) \
+        | (0x04 if content_checksum else 0)
+    desc = bytes([flg, code << 4]) + (b"" if content_size is None else int(content_size).to_bytes(8, "little"))
+    hc = (_xxh32_short(desc) >> 8) & 0xFF if checksum else 0
+    return FRAME_MAGIC.to_bytes(4, "little") + desc + bytes([hc])
+
+
+def parse_frame_header(head: bytes):
+    """The complete descriptor parser: (BlockConfig, FrameConfig, FrameInfo).  Verifies the version, the reserved bits and
+    the header checksum; dictionary ids are not supported.  `head` must hold at least 15 bytes or the whole header."""
+    if len(head) < 7:
+        raise LZ4Error("frame: input ended inside the frame header")
+    magic = int.from_bytes(head[0:4], "little")
+    if magic != FRAME_MAGIC:
+        raise LZ4Error(f"The parsed magic {magic} does not match {FRAME_MAGIC}")
+    flg, bd = head[4], head[5]
+    if (flg >> 6) != 1:
+        raise LZ4Error("Version is not 01")
+    if flg & 0x02 or bd & 0x8F:
+        raise LZ4Error("frame: reserved bits are set")
+    if flg & 0x01:
+        raise LZ4Error("Dict is not yet supported")
+    bs = _BD_CODES.get(bd >> 4)
+    if bs is None:
+        raise LZ4Error("parseBD: Unknown block max size")
+    at, size = 6, None
+    if flg & 0x08:
+        if len(head) < 15:
+            raise LZ4Error("frame: input ended inside the frame header")
+        size = int.from_bytes(head[6:14], "little"); at = 14
+    if head[at] != (_xxh32_short(bytes(head[4:at])) >> 8) & 0xFF:
+        raise LZ4Error("frame: header checksum mismatch")
+    info = FrameInfo(block_checksum=bool(flg & 0x10), content_checksum=bool(flg & 0x04), content_size=size, header_len=at + 1)
+    return BlockConfig(block_size=bs, independent=bool(flg & 0x20)), FrameConfig(has_end_mark=True), info
 
 
 def compress_chunks_frame(cfg: BlockConfig, frame_cfg: FrameConfig, speed: int, chunks: Iterable, **kw) -> Iterator[bytes]:
@@ -573,3 +647,118 @@ def decompress_chunks_with(parser, chunks: Iterable, *, ctx: Optional[Context] =
             yield rest
         yield from it
     return decompress_chunks_raw(cfg, resize_chunks(cfg, frame_cfg, tail()), ctx=ctx, **kw)
+
+
+def write_frame(block_size: BlockSize, speed: int, chunks: Iterable, *, independent: bool = False, block_checksum: bool = False,
+                content_checksum: bool = False, content_size: Optional[int] = None, ctx: Optional[Context] = None, **kw) -> Iterator[bytes]:
+    """A complete LZ4 frame (what the stock `lz4` tool reads): header with its real checksum, one block per input array
+    ([size LE32][LZ4 block][XXH32 of the block iff block_checksum]), end mark, XXH32 of the content iff content_checksum.
+    Arrays must not exceed the block maximum.  Linked blocks use the previous ARRAY as dictionary (the reference's
+    semantics), which every frame decoder accepts.  Checksums are computed on the device; the content checksum needs the
+    whole content in one page-locked buffer."""
+    ctx = ctx or default_context()
+    cfg = BlockConfig(block_size=block_size, independent=independent)
+    yield frame_header(block_size, independent=independent, block_checksum=block_checksum, content_size=content_size,
+                       content_checksum=content_checksum)
+    import collections
+    kept: List[bytes] = []
+    raws = collections.deque()
+
+    def tee(src):
+        for c in src:
+            b = bytes(c)
+            raws.append(b)
+            if content_checksum:
+                kept.append(b)
+            yield b
+
+    def blocks():
+        # a block that did not shrink is STORED: size field with bit 31 set, then the raw bytes (what every frame writer does;
+        # a compressed block may not exceed the block maximum)
+        for blk in compress_chunks(cfg, speed, tee(chunks), ctx=ctx, **kw):
+            raw = raws.popleft()
+            if len(blk) - 4 >= len(raw) and len(raw):
+                yield (len(raw) | 0x80000000).to_bytes(4, "little") + raw
+            else:
+                yield bytes(blk)
+    pending: List[bytes] = []
+    for blk in blocks():
+        if not block_checksum:
+            yield blk
+            continue
+        pending.append(blk)
+        if len(pending) >= 1024:
+            yield from _with_block_checksums(ctx, pending)
+            pending = []
+    if pending:
+        yield from _with_block_checksums(ctx, pending)
+    yield b"\x00\x00\x00\x00"
+    if content_checksum:
+        whole = b"".join(kept)
+        buf = ctx.pinned("f_content", max(len(whole), 1))
+        buf[:len(whole)] = np.frombuffer(whole, dtype=np.uint8)
+        yield int(ctx.xxh32(buf[:max(len(whole), 1)], [0], [len(whole)])[0]).to_bytes(4, "little")
+
+
+def _with_block_checksums(ctx: Context, blocks: Sequence[bytes]) -> Iterator[bytes]:
+    src, offs, lens = _gather(ctx, "f_blocks", blocks)
+    sums = ctx.xxh32(src, offs + 4, lens - 4)                    # the checksum covers the block data, not its size field
+    for b, h in zip(blocks, sums):
+        yield b + int(h).to_bytes(4, "little")
+
+
+def read_frame(chunks: Iterable, *, ctx: Optional[Context] = None, verify: bool = True, **kw) -> Iterator[bytes]:
+    """Decode one complete LZ4 frame from an arbitrarily fragmented byte stream: header (checksum verified), blocks
+    (stored blocks pass through as literal-only LZ4 blocks, so a linked chain stays intact), block checksums, end
+    mark, content size and content checksum.  Yields one array per block."""
+    ctx = ctx or default_context()
+    data = b"".join(bytes(c) for c in chunks)
+    cfg, _, info = parse_frame_header(data[:15])
+    at = info.header_len
+    framed: List[bytes] = []
+    check_off, check_len, check_want = [], [], []
+    while True:
+        if at + 4 > len(data):
+            raise LZ4Error("resizeChunksD: No end mark found")
+        size = int.from_bytes(data[at:at + 4], "little")
+        at += 4
+        if size == 0:
+            break
+        stored, n = bool(size >> 31), size & 0x7FFFFFFF
+        if n > cfg.max_block_size or at + n > len(data):
+            raise LZ4Error("resizeChunksD: Incomplete block")
+        body = data[at:at + n]
+        if info.block_checksum:
+            check_off.append(at); check_len.append(n); check_want.append(int.from_bytes(data[at + n:at + n + 4], "little"))
+            at += 4
+        at += n
+        if stored:                                               # token, length bytes, literals: decodes to `body` itself
+            m = len(body)
+            if m < 15:
+                body = bytes([m << 4]) + body
+            else:
+                q, r = divmod(m - 15, 255)
+                body = b"\xf0" + b"\xff" * q + bytes([r]) + body
+        framed.append(len(body).to_bytes(4, "little") + body)
+    if verify and check_want:
+        buf = ctx.pinned("f_in", len(data))
+        buf[:len(data)] = np.frombuffer(data, dtype=np.uint8)
+        got = ctx.xxh32(buf[:len(data)], check_off, check_len)
+        bad = np.nonzero(got != np.array(check_want, dtype=np.uint32))[0]
+        if len(bad):
+            raise LZ4Error(f"frame: block checksum mismatch in block {int(bad[0])}")
+    total, outs = 0, []
+    for a in decompress_chunks_raw(cfg, framed, ctx=ctx, **kw):
+        total += len(a)
+        if info.content_checksum and verify:
+            outs.append(a)
+        yield a
+    if info.content_size is not None and info.content_size != total:
+        raise LZ4Error(f"frame: content size {total} does not match the header's {info.content_size}")
+    if info.content_checksum and verify:
+        want = int.from_bytes(data[at:at + 4], "little")
+        whole = b"".join(outs)
+        buf = ctx.pinned("f_content", max(len(whole), 1))
+        buf[:len(whole)] = np.frombuffer(whole, dtype=np.uint8)
+        if int(ctx.xxh32(buf[:max(len(whole), 1)], [0], [len(whole)])[0]) != want:
+            raise LZ4Error("frame: content checksum mismatch")

@@ -967,6 +967,42 @@ int b200lz4_compact_dev(const void* d_slots, const int64_t* d_slot_off, const in
     return 0;
 }
 
+// ------------------------------------------------------------------ checksums
+int b200lz4_xxh32_dev(const void* d_buf, const int64_t* d_off, const int32_t* d_len, int n, uint32_t seed, uint32_t* d_out, void* cuda_stream)
+{
+    if (n < 0 || (n > 0 && (!d_buf || !d_off || !d_len || !d_out))) return fail(B200LZ4_E_ARG, "NULL argument");
+    CU(launch_xxh32(static_cast<const uint8_t*>(d_buf), d_off, d_len, n, seed, d_out, static_cast<cudaStream_t>(cuda_stream)));
+    return 0;
+}
+
+int b200lz4_xxh32_batch(b200lz4_ctx* c, const void* src, int64_t src_bytes, const int64_t* off, const int32_t* len, int n,
+                        uint32_t seed, uint32_t* out)
+{
+    if (!c) return fail(B200LZ4_E_ARG, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!off || !len || !out))) return fail(B200LZ4_E_ARG, "NULL argument");
+    if (n == 0) return 0;
+    int rc;
+    if ((rc = check_blocks(off, len, n, src_bytes))) return rc;
+    CU(cudaSetDevice(c->device));
+    Carver cv;
+    const size_t o_off = cv.take(sizeof(int64_t) * n), o_len = cv.take(sizeof(int32_t) * n), o_up = cv.off, o_out = cv.take(sizeof(uint32_t) * n);
+    if ((rc = c->h_desc.ensure(cv.off))) return rc;
+    if ((rc = c->d_desc.ensure(cv.off))) return rc;
+    if ((rc = c->d_src.ensure((size_t)src_bytes + 64))) return rc;
+    uint8_t* hd = static_cast<uint8_t*>(c->h_desc.p); uint8_t* dd = static_cast<uint8_t*>(c->d_desc.p);
+    memcpy(hd + o_off, off, sizeof(int64_t) * n); memcpy(hd + o_len, len, sizeof(int32_t) * n);
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(dd, hd, o_up, cudaMemcpyHostToDevice, st));
+    if (src_bytes) CU(cudaMemcpyAsync(c->d_src.p, src, (size_t)src_bytes, cudaMemcpyHostToDevice, st));
+    CU(launch_xxh32(static_cast<const uint8_t*>(c->d_src.p), reinterpret_cast<const int64_t*>(dd + o_off), reinterpret_cast<const int32_t*>(dd + o_len),
+                    n, seed, reinterpret_cast<uint32_t*>(dd + o_out), st));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(hd + o_out, dd + o_out, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(out, hd + o_out, sizeof(uint32_t) * n);
+    return 0;
+}
+
 // ------------------------------------------------------------------ re-frame
 // resizeChunksD's `process` (src/Streamly/Internal/LZ4.hs:459-484) applied to one contiguous range.
 int b200lz4_reframe(const void* buf, int64_t len, int header_mode, int has_end_mark,

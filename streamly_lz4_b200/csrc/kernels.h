@@ -51,6 +51,7 @@ cudaError_t device_sm_count(int* out);
 cudaError_t launch_compact(const CompactArgs& a, cudaStream_t stream);
 cudaError_t launch_reframe(const uint8_t* buf, int64_t len, int header, int has_end_mark,
                            int64_t* block_off, int32_t* block_len, int64_t max_blocks, int64_t* result, cudaStream_t stream);
+cudaError_t launch_xxh32(const uint8_t* buf, const int64_t* off, const int32_t* len, int n, uint32_t seed, uint32_t* out, cudaStream_t stream);
 int kernel_launches_per_compress();
 int kernel_launches_per_decompress();
 int kernel_launches_per_compact();

@@ -147,7 +147,7 @@ def test_frame_header_parser_mirrors_the_reference():
     assert cfg.block_size is lz.BlockSize.BlockMax64KB and cfg.meta_size == 4 and fc.has_end_mark and not cfg.independent
     for code, bs in ((4, "BlockMax64KB"), (5, "BlockMax256KB"), (6, "BlockMax1MB"), (7, "BlockMax4MB")):
         assert lz.simple_frame_parser(ok[:5] + bytes([code << 4, 0]))[0].block_size is lz.BlockSize[bs]
-        assert lz.frame_header(lz.BlockSize[bs]) == ok[:5] + bytes([code << 4, 0])
+        assert lz.frame_header(lz.BlockSize[bs], checksum=False) == ok[:5] + bytes([code << 4, 0])
     bad = [(bytes([5, 34, 77, 24, 64, 64, 0]), "does not match 407708164"),
            (ok[:4] + bytes([0x80, 64, 0]), "Version is not 01"), (ok[:4] + bytes([0x00, 64, 0]), "Version is not 01"),
            (ok[:4] + bytes([0x60, 64, 0]), "Block independence is not yet supported"),
@@ -180,3 +180,31 @@ def test_gather_host_is_a_parallel_memcpy(built):
         assert lib.b200lz4_gather_host(dst.ctypes.data, ptrs.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(arrays), threads) == 0
         for a, o in zip(arrays, offs):
             assert np.array_equal(dst[o:o + a.size], a)
+
+
+def test_complete_frame_descriptor(built):
+    """The descriptor beyond the reference's stub: the headers the stock `lz4` tool writes (known answers), every flag,
+    header-checksum verification, reserved bits."""
+    import streamly_lz4_b200 as lz
+    from oracle import frame as oframe
+    B = lz.BlockSize
+    assert lz.frame_header(B.BlockMax64KB, independent=True).hex() == "04224d18604082"
+    assert lz.frame_header(B.BlockMax64KB, independent=True, content_checksum=True).hex() == "04224d186440a7"
+    assert lz.frame_header(B.BlockMax4MB, independent=True, content_checksum=True).hex() == "04224d186470b9"
+    for bs, code in ((B.BlockMax64KB, 4), (B.BlockMax256KB, 5), (B.BlockMax1MB, 6), (B.BlockMax4MB, 7)):
+        for ind in (False, True):
+            for bc in (False, True):
+                for cc in (False, True):
+                    for size in (None, 0, 123456789012):
+                        h = lz.frame_header(bs, independent=ind, block_checksum=bc, content_checksum=cc, content_size=size)
+                        assert h == oframe.header(code, ind, bc, size, cc)
+                        cfg, fc, info = lz.parse_frame_header(h + bytes(8))
+                        assert (cfg.block_size, cfg.independent, fc.has_end_mark) == (bs, ind, True)
+                        assert (info.block_checksum, info.content_checksum, info.content_size, info.header_len) == (bc, cc, size, len(h))
+                        bad = bytearray(h); bad[-1] ^= 1
+                        with pytest.raises(lz.LZ4Error, match="header checksum"):
+                            lz.parse_frame_header(bytes(bad) + bytes(8))
+    with pytest.raises(lz.LZ4Error, match="reserved"):
+        lz.parse_frame_header(bytes.fromhex("04224d18624000"))
+    with pytest.raises(lz.LZ4Error, match="Dict"):
+        lz.parse_frame_header(bytes.fromhex("04224d18614000") + bytes(8))

@@ -284,6 +284,23 @@ def test_c_example_links_and_round_trips(ctx):
     assert "batched : " in out.stdout and "legacy  : " in out.stdout
 
 
+def test_haskell_shim_call_sequences_replayed_in_c(ctx):
+    """examples/ffi_replay.c: the foreign-call sequences of haskell/Streamly/Internal/LZ4/B200.hs (which cannot be compiled
+    here: no GHC) with the shim's exact argument marshalling -- compressChunksD, resizeChunksD over b200lz4_reframe,
+    decompressChunksRawD; linked (persistent stream handles across batches) and independent (NULL stream table)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "ffi_replay")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    lib_dir = os.path.join(root, "streamly_lz4_b200")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "ffi_replay.c"),
+                           "-L" + lib_dir, "-lb200lz4", "-Wl,-rpath," + lib_dir, "-o", exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout
+    assert "linked     : 37 arrays" in out.stdout and "independent: 37 arrays" in out.stdout
+
+
 def test_framed_stream_with_header_and_end_mark(ctx, ref):
     """benchmark/Main.hs:85-118 + decompressChunksWithD (Internal/LZ4.hs:569-577): 7-byte frame header, BlockMax64KB blocks
     (4-byte block headers), 4-byte end mark, junk after it; re-read at several buffer sizes."""
@@ -291,7 +308,7 @@ def test_framed_stream_with_header_and_end_mark(ctx, ref):
     from streamly_lz4_b200 import datagen
     d = datagen.make("text", 91, 1 << 20)
     arrays = split(d, 65536)
-    hdr = lz.frame_header(lz.BlockSize.BlockMax64KB)
+    hdr = lz.frame_header(lz.BlockSize.BlockMax64KB, checksum=False)          # HC = 0, as benchmark/Main.hs:92-100 writes it
     cfg, fc = lz.simple_frame_parser(hdr)
     body = list(lz.compress_chunks_frame(cfg, fc, 65537, arrays, ctx=ctx))
     assert body[-1] == b"\0\0\0\0"

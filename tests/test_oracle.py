@@ -169,3 +169,41 @@ def test_resize_restatement_end_mark_and_errors(port):
     with pytest.raises(RuntimeError, match="Incomplete block"):
         resize_chunks([blob[:-3]])
     assert resize_chunks([]) == []
+
+
+def test_xxh32_known_answers(built):
+    """XXH32 restated in oracle/lz4_oracle.c against published known answers, and the frame-header checksum bytes of the
+    headers the stock `lz4` tool writes (04 22 4D 18 60 40 82 / 64 40 A7 / 64 70 B9)."""
+    from oracle import frame
+    assert frame.xxh32(b"") == 0x02CC5D05
+    assert frame.xxh32(b"a") == 0x550D7456
+    assert frame.xxh32(b"abc") == 0x32D153FF
+    assert frame.xxh32(b"Nobody inspects the spammish repetition") == 0xE2293B2F
+    for desc, hc in ((b"\x60\x40", 0x82), (b"\x64\x40", 0xA7), (b"\x64\x70", 0xB9)):
+        assert (frame.xxh32(desc) >> 8) & 0xFF == hc
+    assert frame.header(4, independent=True, content_checksum=True).hex() == "04224d186440a7"
+
+
+def test_frame_restatement_round_trips(built):
+    """oracle/frame.py: encode -> parse -> decode over every flag combination, stored (incompressible) blocks included;
+    corrupted checksums are rejected."""
+    import numpy as np
+    from oracle import frame
+    from oracle.oracle import Oracle
+    from streamly_lz4_b200 import datagen
+    ora = Oracle("auto")
+    data = datagen.make("mixed", 17, 5 * 65536 + 1234).tobytes()
+    arrays = [data[i:i + 65536] for i in range(0, len(data), 65536)]
+    for ind in (False, True):
+        for bc in (False, True):
+            for cs in (False, True):
+                for cc in (False, True):
+                    blob = frame.encode(ora, arrays, 4, 1, ind, bc, cs, cc)
+                    d, blocks, _ = frame.parse(blob)
+                    assert d["frame_bytes"] == len(blob) and len(blocks) == len(arrays)
+                    assert any(stored for stored, _ in blocks)              # the random segment is stored uncompressed
+                    assert frame.decode(ora, blob) == data
+    blob = bytearray(frame.encode(ora, arrays, 4, 1, False, True, False, True))
+    blob[40] ^= 1
+    with pytest.raises(ValueError):
+        frame.decode(ora, bytes(blob))
