@@ -446,7 +446,7 @@ def run_gpu(args):
         arrays = [host[o:o + l].copy() for o, l in zip(offs, lens)]         # separately allocated pageable arrays
         cfg = lz.BlockConfig(independent=True)
         sizes = 0
-        for a in lz.compress_chunks(cfg, ACCEL, arrays, ctx=ctx, copy=False):
+        for a in lz.compress_chunks(cfg, ACCEL, arrays, ctx=ctx, copy=False, batch_bytes=512 << 20):
             sizes += len(a)
         assert sizes == comp_total, (sizes, comp_total)
         reps = max(2, min(args.steps, 5))
@@ -454,12 +454,12 @@ def run_gpu(args):
         l0 = ctx.launch_count()
         t_s0 = time.perf_counter()
         for _ in range(reps):
-            for a in lz.compress_chunks(cfg, ACCEL, arrays, ctx=ctx, copy=False):
+            for a in lz.compress_chunks(cfg, ACCEL, arrays, ctx=ctx, copy=False, batch_bytes=512 << 20):
                 pass
         barrier()
         staged_wall = (time.perf_counter() - t_s0) / reps
         staged = {"wall_ms_per_step": 1e3 * rmax(staged_wall), "launches": ctx.launch_count() - l0,
-                  "api": "streamly_lz4_b200.compress_chunks(copy=False) over 1678 pageable numpy arrays: multi-threaded gather "
+                  "api": "streamly_lz4_b200.compress_chunks(copy=False, batch_bytes=512 MiB) over 1678 pageable numpy arrays: multi-threaded gather "
                          "into pinned memory (b200lz4_gather_host) one batch ahead of b200lz4_compress_batch; outputs are "
                          "slices of the pinned result"}
         del arrays

@@ -474,9 +474,11 @@ cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream)
     static const char* wide_env = getenv("B200LZ4_DWIDE");           // A/B switch: "0" never, "1" whenever the arena allows
     DecompressArgs b = a;
     b.debug = dbg ? atoi(dbg) : 0;
-    // Wide kernel (one stream per SM, parallel block parsers + out-of-order copiers): linked streams when there are
-    // few enough of them that the narrow kernel would leave most of the GPU idle; few independent blocks likewise.
-    bool wide = a.stream_first ? (a.n_streams <= 2 * sm_count) : (a.n_streams <= sm_count);
+    // Wide kernel (one stream per SM: parallel block parsers + a copier pipeline): LINKED streams when there are few enough of
+    // them that the narrow kernel would leave most of the GPU idle (measured: 128 streams 17 -> 35 GB/s on mixed data, 11 ->
+    // 49 GB/s on text; with more than two streams per SM the narrow kernel's 16 CTAs per SM win).  Independent blocks gain
+    // nothing from it -- a block has ONE token chain, so only one of the eight parsers would work.
+    bool wide = a.stream_first != nullptr && a.n_streams <= 2 * sm_count;
     if (wide_env) wide = wide_env[0] == '1';
     if (wide && a.wide_arena) return launch_decompress_wide(b, sm_count, stream);
     const int max_ctas = sm_count * 16;

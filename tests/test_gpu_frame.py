@@ -9,8 +9,8 @@ pytestmark = pytest.mark.gpu
 def test_xxh32_kernel_matches_the_restatement(ctx):
     from oracle import frame
     rng = np.random.default_rng(3)
-    buf = ctx.pinned("x_buf", 3 << 20)
-    buf[:3 << 20] = rng.integers(0, 256, 3 << 20, dtype=np.uint8)
+    buf = ctx.pinned("x_buf", 12 << 20)
+    buf[:12 << 20] = rng.integers(0, 256, 12 << 20, dtype=np.uint8)
     lens = [0, 1, 3, 4, 5, 15, 16, 17, 31, 32, 33, 63, 64, 511, 512, 513, 4096, 65536, 640000, 1 << 20]
     lens += [int(x) for x in rng.integers(0, 70000, 200)]
     offs, at = [], 0
