@@ -15,7 +15,7 @@ HOSTT  := $(PKG)/csrc/host_mirror_test
 CU_SRCS  := $(wildcard $(CSRC)/*.cu)
 CU_HDRS  := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.hpp) include/b200lz4.h
 
-all: $(LIB) $(GEN) oracle
+all: $(LIB) $(BOUNDS) $(GEN) oracle
 
 $(LIB): $(CU_SRCS) $(CU_HDRS)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRCS) 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
@@ -27,16 +27,22 @@ $(GEN): $(PKG)/datagen/datagen.c
 oracle:
 	$(MAKE) -s -C oracle
 
+# debug build of the same library with destination-bounds checks in the decoder kernels (tests/test_gpu_modes.py)
+BOUNDS := $(PKG)/libb200lz4_bounds.so
+bounds: $(BOUNDS)
+$(BOUNDS): $(CU_SRCS) $(CU_HDRS)
+	$(NVCC) $(NVFLAGS) -DB200LZ4_BOUNDS_CHECK -shared -o $@ $(CU_SRCS) 2> /dev/null
+
 # development build with cycle accounting in the wide decoder (load it with B200LZ4_LIB=build/libb200lz4_stats.so)
 stats: $(CU_SRCS) $(CU_HDRS)
 	mkdir -p build
 	$(NVCC) $(NVFLAGS) -DB200LZ4_WIDE_STATS -shared -o build/libb200lz4_stats$(SUFFIX).so $(CU_SRCS) 2> build/ptxas_stats.log || (cat build/ptxas_stats.log; false)
 
 clean:
-	rm -f $(LIB) $(GEN) $(CSRC)/ptxas.log
+	rm -f $(LIB) $(BOUNDS) $(GEN) $(CSRC)/ptxas.log
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean stats
+.PHONY: all oracle clean stats bounds
 
 # plain-C example over the C ABI (needs a B200 to run)
 examples: $(LIB)

@@ -224,7 +224,7 @@ def run_reference(args):
                                        f"mean of {args.steps} steps (best step {best:.2f} GB/s)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "extra": extra}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -515,6 +515,36 @@ def run_gpu(args):
             del B1
             del text
             gpu_launches_extra += 5 * 2 * (steps_x + 1) + 2 * 2 * 3 + 7
+    # ---- one batch striped over all N GPUs by ONE process (b200lz4_mctx): rank 0 drives every device, the other ranks wait
+    if world > 1 and not args.no_extras:
+        barrier()
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                m = lz.MultiContext(list(range(world)))
+                many = ctx.pinned("b_many", int((bound + HEADER).sum()))
+                rc, offm, lenm = m.compress_batch(src_view, offs, lens, ACCEL, HEADER, many)
+                assert rc == 0, m.last_error()
+                t_m = []
+                for _ in range(3):
+                    t1 = time.perf_counter()
+                    rc, offm, lenm = m.compress_batch(src_view, offs, lens, ACCEL, HEADER, many)
+                    t_m.append(time.perf_counter() - t1)
+                same = bool(np.array_equal(lenm, olen)) and all(
+                    many[offm[i]:offm[i] + HEADER + lenm[i]].tobytes() == pin_dst[doff[i]:doff[i + 1]].tobytes() for i in (0, n // 2, n - 1))
+                extra["mctx_one_process"] = {
+                    "what": f"b200lz4_compress_batch_multi: ONE {args.size_mib} MiB batch (rank 0's stripe) cut into {world} block ranges, one host "
+                            f"thread + ctx per GPU, pinned host in/out; strong scaling of the end-to-end call",
+                    "value": total / min(t_m) / 1e9, "unit": UNIT, "wall_ms": 1e3 * min(t_m), "identical_to_single_gpu": same,
+                    "per_device_ms": [m.timing(i) for i in range(m.size)]}
+                gpu_launches_extra += 3 * 4 * world
+                m.close()
+            except Exception as e:                  # reported, never fatal for the headline
+                extra["mctx_one_process"] = {"error": repr(e)}
+            store.set("b200lz4_mctx_done", "1")
+        else:
+            store.wait(["b200lz4_mctx_done"])       # on the CPU: an NCCL barrier would park a kernel on this rank's SMs
+        barrier()
     # ---- config 3 (strong scaling, N > 1 or --config3): d+640000 of an 8 GiB pre-compressed stream, 8 GiB / N per rank
     if (world > 1 or args.config3) and not args.no_extras:
         extra["config3_strong"] = run_config3(args, torch, dist, lib, lz, ctx, dev, stream, rank, world, peak, barrier, rmax)
@@ -593,7 +623,7 @@ def run_gpu(args):
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
             "extra": {k: v for k, v in extra.items() if v is not None},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -670,6 +700,25 @@ def run_config3(args, torch, dist, lib, lz, ctx, dev, stream, rank, world, peak,
                     "what": "pinned host stream -> b200lz4_reframe (host header walk) -> b200lz4_decompress_batch -> pinned host output"}}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Point file descriptor 1 at stderr while the benchmark runs (NCCL prints a version banner to stdout); emit() writes
+    the one JSON line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -687,6 +736,7 @@ def main():
     import __graft_entry__ as ge
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         ge.build_cpu_side()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

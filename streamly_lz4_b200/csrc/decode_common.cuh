@@ -16,6 +16,16 @@ namespace b200lz4 {
 
 namespace dec {
 
+// Debug build (make bounds -> streamly_lz4_b200/libb200lz4_bounds.so, exercised by tests/test_gpu_modes.py): every global
+// store range of the decoder is checked against the destination capacity of its block; a violation records the source
+// line in the scratch block and traps.  compute-sanitizer is not available on the GPU pool, so this is the memory-safety
+// evidence for malformed input.  Compiled out of the product.
+#ifdef B200LZ4_BOUNDS_CHECK
+#define BCHK(a, cond) do { if (!(cond)) { atomicExch(&(a).scratch->pad_[59], (uint32_t)__LINE__); __trap(); } } while (0)
+#else
+#define BCHK(a, cond) do { } while (0)
+#endif
+
 constexpr int kInRing = 4096;            // bytes of compressed payload resident in shared memory
 constexpr int kFill = 512;               // ring fill unit (32 lanes x 16 bytes)
 constexpr int kOutRing = 8192;           // bytes of recent output resident in shared memory

@@ -671,6 +671,9 @@ __device__ void wstage_flush(const DecompressArgs& a, int w, WCtl* ctl, uint32_t
         const uint32_t s_pos = k.base + k.op_start;
         if (e != s_pos) {
             if (k.blk != cached_blk) { blk_out = a.dst + a.dst_off[k.blk]; cached_blk = k.blk; }
+#ifdef B200LZ4_BOUNDS_CHECK
+            { const BlockGeom g = block_geom(a, k.blk); BCHK(a, (long long)k.op_start + (e - s_pos) <= (long long)g.cap && (e - s_pos) <= 65536u); }
+#endif
             flush_r2g(out_s, blk_out + k.op_start, s_pos, e - s_pos);
         }
         __threadfence_block();

@@ -41,3 +41,19 @@ def test_parity_with_forced_kernel(ctx, env):
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:]
     assert " passed" in out.stdout
+
+
+def test_decoder_bounds_checked_build_on_malformed_input(ctx):
+    """compute-sanitizer is not available on the GPU pool, so memory safety of the decoders on hostile input is shown with
+    a debug build (make bounds: -DB200LZ4_BOUNDS_CHECK) that checks every destination range against the block capacity
+    and traps on a violation: the hand-built, corrupted and malformed-block tests run through it, narrow and wide."""
+    lib = os.path.join(ROOT, "streamly_lz4_b200", "libb200lz4_bounds.so")
+    if not os.path.exists(lib):
+        pytest.skip("libb200lz4_bounds.so not built (make bounds)")
+    for wide in ("0", "1"):
+        e = dict(os.environ, B200LZ4_LIB=lib, B200LZ4_DWIDE=wide)
+        out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_fuzz.py", "tests/test_gpu_parity.py",
+                              "-k", "handbuilt or corrupted or malformed or edge_sizes or echoing"], cwd=ROOT, env=e,
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+        assert out.returncode == 0, out.stdout[-3000:]
+        assert " passed" in out.stdout
