@@ -6,7 +6,7 @@ timeout 900 python -m pytest -x -q -m gpu tests/test_gpu_multi.py > gpurun_out/p
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_${tag}.err | cut -c1-300
 python - <<PY
 import json
-d=json.load(open("gpurun_out/bench_${tag}.json"))
+d=[json.loads(l) for l in open("gpurun_out/bench_${tag}.json") if l.startswith("{")][-1]
 print("N",d["n_gpus"],"value",round(d["value"],1),"e2e",round(d["e2e"]["value"],1),"ceil",round(d["e2e"]["copy_ceiling"]["value"],1),"frac",round(d["e2e"]["frac_of_copy_ceiling"],2),"staged",d["e2e_staged"] and round(d["e2e_staged"]["value"],1))
 for k in ("mctx_one_process","config3_strong","d+640000"):
     print(k, json.dumps(d["extra"].get(k))[:700])
