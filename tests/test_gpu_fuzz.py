@@ -261,3 +261,55 @@ def test_echoing_linked_streams_wide_and_dense(ctx, ref, seed):
         rc, boff, blen = ctx.decompress_batch(comp, doff[:-1].copy(), np.diff(doff).astype(np.int32), 8, 0, back, stream_first=sf)
         assert rc == 0 and (blen == lens).all()
         assert back[:int(lens.sum())].tobytes() == b"".join(arrays)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_corrupted_block_inside_a_linked_stream(ctx, ref, seed):
+    """A block that fails in the MIDDLE of a linked stream must not disturb the chain: LZ4_decompress_safe_continue returns
+    before it touches the stream state (cbits/lz4.c:2353 `if (result <= 0) return result`), so the next block still sees the
+    last GOOD output as its dictionary.  The batch call reports the failure per block and goes on; the same call sequence
+    on the reference's own lz4.c (one LZ4_streamDecode_t, LZ4_decompress_safe_continue per block) is the expectation.  In
+    the wide decoder this is the path that restarts the shared-memory ring from global memory."""
+    import ctypes
+    import streamly_lz4_b200 as lz
+    from streamly_lz4_b200 import datagen
+    rng = np.random.default_rng(7000 + seed + SHIFT)
+    bs = int(rng.choice([3000, 65536, 200000]))
+    data = datagen.make(["text", "mixed", "records", "sparse01"][seed % 4], 80 + seed, 6 * bs)
+    arrays = [data[i:i + bs].tobytes() for i in range(0, data.size, bs)]
+    good = ref.compress_chunks(arrays, 1, linked=True)                       # blocks 0..5, each with its predecessor as dictionary
+    skip = ref.compress_chunks([arrays[1], arrays[3]], 1, linked=True)[1]    # block 3 compressed against block 1
+    half = good[2][8:8 + (len(good[2]) - 8) // 2]                             # a truncated payload: fails (input ends inside a sequence)
+    junk = len(half).to_bytes(4, "little") + good[2][4:8] + half
+    garbage = (24).to_bytes(4, "little") + (bs).to_bytes(4, "little") + bytes(rng.integers(0, 256, 24, dtype=np.uint8))
+    stream = [good[0], good[1], bytes(junk), garbage, skip, good[4]]         # good[4] needs block 3's plaintext as dictionary
+    # the reference, call by call
+    framed_arena, ptrs, lens = ref.lay_out(stream)
+    ds = ref.dcreate()
+    outs = [np.zeros(bs + 64, dtype=np.uint8) for _ in stream]               # separate, non-adjacent output arrays
+    want_len, want = [], []
+    for i, f in enumerate(stream):
+        cap = int.from_bytes(f[4:8], "little", signed=True)
+        r = ref.dcont(ds, int(ptrs[i]) + 8, outs[i].ctypes.data, len(f) - 8, cap)
+        want_len.append(r); want.append(outs[i][:max(r, 0)].tobytes())
+    ref.dfree(ds)
+    assert want_len[0] == bs and want_len[1] == bs and want_len[2] < 0 and want_len[3] < 0
+    assert want_len[4] == bs and want[4] == arrays[3] and want[5] == arrays[4]     # the chain survived the two failures
+    # here, in one batch and split over two calls (the state crosses the call after the failed blocks)
+    for cut in (len(stream), 4):
+        dstream = lz.DecompressStream(ctx)
+        got_len, got = [], []
+        for part in (stream[:cut], stream[cut:]):
+            if not part:
+                continue
+            src, offs, plens = lz.api._gather(ctx, "t_src", part)
+            dst = ctx.pinned("t_dst", (bs + 64) * len(part))
+            rc, doff, olen = ctx.decompress_batch(src, offs, plens, 8, 0, dst, np.array([0, len(part)], dtype=np.int32), [dstream])
+            assert rc in (0, -4)
+            for k in range(len(part)):
+                got_len.append(int(olen[k])); got.append(dst[doff[k]:doff[k] + max(int(olen[k]), 0)].tobytes())
+        dstream.free()
+        for i in range(len(stream)):
+            assert (got_len[i] < 0) == (want_len[i] < 0), f"block {i}: {got_len[i]} vs reference {want_len[i]}"
+            if want_len[i] >= 0:
+                assert got_len[i] == want_len[i] and got[i] == want[i], f"block {i} differs (cut {cut})"
