@@ -75,16 +75,21 @@ constexpr uint32_t kSeedBase = 65536;             // stream position of the firs
 struct WTicket { uint32_t jn, cf, op_start, base, valid_lo; int blk; uint32_t safe, aux; };   // 32 bytes; jn = parser << 16 | ring slot; safe: everything below is final for stage F
 
 struct WCtl {                                     // shared memory
-    uint32_t near_next;                           // stage N: tickets below this are complete in the ring
+    uint32_t pad0_;
     uint32_t finished;                            // dispatcher: no more tickets will be issued
     uint32_t t_final;                             // ... and this many were
     uint32_t pad_;
     uint32_t rd[kWP];                             // dispatcher: next batch of each parser ring to hand out
     uint32_t wr_pub[kWP];                         // parsers: batches published
     uint32_t cons[kWP];                           // dispatcher: batches retired (parsers wait on it for ring space)
-    uint32_t tready[kTickets];                    // dispatcher: ticket t issued <=> tready[t % 64] == t + 1
+    // One mbarrier per ticket slot and pipeline edge (count 1; ticket t uses phase (t / 64) & 1 of slot t % 64).  Waiting on an
+    // mbarrier suspends the warp in hardware; polling flags with nanosleep() instead let a dozen idle warps issue more
+    // instructions than the working ones (ncu: 11 G of 14 G warp instructions were polls).
+    unsigned long long bar_ticket[kTickets];      // dispatcher -> all stages: ticket t has been issued
+    unsigned long long bar_lit[kTickets];         // stage L -> F: descriptors in shared memory, literals in the ring
+    unsigned long long bar_far[kTickets];         // stage F -> N
+    unsigned long long bar_near[kTickets];        // stage N -> F (ticket t + kWDepth + 1 may copy its far matches) and G
     uint32_t near_mask[kWSlots], near_long[kWSlots];      // stage F -> N: which sequences of the batch have a near match / the batch is a long match piece
-    uint32_t lit_done[kTickets], far_done[kTickets];      // stages L / F: ticket t done <=> flag[t % 64] == t + 1
     uint32_t done[kTickets];                      // stage G: ticket t is in global memory <=> done[t % 64] == t + 1
     uint32_t tend[kTickets], tn[kTickets], tj[kTickets];      // dispatcher-private: end position / ring slot / parser of a ticket
     WTicket ticket[kTickets];
@@ -415,7 +420,7 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
                     WTicket* tk = &ctl->ticket[k];
                     tk->jn = (j << 16) | (n & (kWR - 1)); tk->cf = h.x; tk->op_start = h.y; tk->base = base; tk->valid_lo = valid_lo; tk->blk = blk; tk->safe = hist[kWDepth - 1]; tk->aux = h.w;
                     __threadfence_block();
-                    vst(&ctl->tready[k], D.T + 1);
+                    mbar_arrive(&ctl->bar_ticket[k]);
                 }
                 __syncwarp();
                 D.T++;
@@ -469,17 +474,31 @@ __device__ void wdispatch_main(const DecompressArgs& a, WCtl* ctl, uint32_t out_
 }
 
 // ---------------------------------------------------------------------- copiers ----
-// wait until flag[t % 64] == t + 1
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t t)
-{ while (vld(&flag[t & (kTickets - 1)]) != t + 1) __nanosleep(20); __threadfence_block(); }
+// one attempt to wait (suspended in hardware for up to ~1 us) for the phase of ticket t on its slot's barrier
+__device__ __forceinline__ bool bar_try(unsigned long long* bars, uint32_t t)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(&bars[t & (kTickets - 1)])), "r"((t >> 6) & 1u), "r"(1000u) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bar_wait(unsigned long long* bars, uint32_t t) { while (!bar_try(bars, t)) { } }
+// all lanes' earlier writes, then one arrival for ticket t
+__device__ __forceinline__ void bar_signal(unsigned long long* bars, uint32_t t)
+{
+    __threadfence_block();
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(&bars[t & (kTickets - 1)]);
+}
 // wait until ticket t has been issued; false: the dispatcher has finished and never issued it
 __device__ __forceinline__ bool wait_ticket(WCtl* ctl, uint32_t t)
 {
-    while (vld(&ctl->tready[t & (kTickets - 1)]) != t + 1) {
+    while (!bar_try(ctl->bar_ticket, t))
         if (vld(&ctl->finished) && (int)(t - vld(&ctl->t_final)) >= 0) return false;
-        __nanosleep(40);
-    }
-    __threadfence_block();
     return true;
 }
 struct WTk { uint32_t j, slot, base, op_start, valid_lo, safe, aux; int cf, blk; };
@@ -543,9 +562,7 @@ __device__ void wstage_literals(const DecompressArgs& a, int w, WCtl* ctl, uint3
                 else { const uint8_t* gp = blk_gbase + d.x; for (uint32_t i = 0; i < lit; i++) sts8(out_s + ((lit_pos + i) & M), (uint32_t)__ldg(gp + i)); }
             }
         }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) vst(&ctl->lit_done[t & (kTickets - 1)], t + 1);
+        bar_signal(ctl->bar_lit, t);
         WSTAT(2)
     }
     WSTAT_FLUSH(a, 8, 4)
@@ -567,7 +584,7 @@ __device__ void wstage_far(const DecompressArgs& a, int w, WCtl* ctl, uint32_t o
         const uint32_t dslot = desc_s + (t & (kWSlots - 1)) * 512u;
         uint32_t nmask = 0, nlong = 0;
         if (cnt) {
-            wait_flag(ctl->lit_done, t);                                    // (the descriptors are in shared memory)
+            bar_wait(ctl->bar_lit, t);                                      // (the descriptors are in shared memory)
             WSTAT(0)
             const uint4 d = lds128(dslot + 16u * lane);
             if (k.cf & kBulk) {
@@ -590,20 +607,14 @@ __device__ void wstage_far(const DecompressArgs& a, int w, WCtl* ctl, uint32_t o
                 }
                 // everything below `safe` (the start of ticket t - kWDepth) is final once stage N has finished ticket t - kWDepth - 1
                 if (__ballot_sync(kFull, far)) {
-                    while ((int)(vld(&ctl->near_next) + (uint32_t)kWDepth - t) < 0) __nanosleep(20);
-                    __threadfence_block();
+                    if (t > (uint32_t)kWDepth) bar_wait(ctl->bar_near, t - kWDepth - 1);
                     WSTAT(1)
                     if (far) lane_copy4(out_s, m_pos, out_s, from, kWM, mlen);
                 }
             }
         }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) {
-            vst(&ctl->near_mask[t & (kWSlots - 1)], nmask); vst(&ctl->near_long[t & (kWSlots - 1)], nlong);
-            __threadfence_block();
-            vst(&ctl->far_done[t & (kTickets - 1)], t + 1);
-        }
+        if (lane == 0) { vst(&ctl->near_mask[t & (kWSlots - 1)], nmask); vst(&ctl->near_long[t & (kWSlots - 1)], nlong); }
+        bar_signal(ctl->bar_far, t);
         WSTAT(2)
     }
     WSTAT_FLUSH(a, 12, 3)
@@ -618,12 +629,9 @@ __device__ void wstage_near(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, 
     WSTAT_DECL(4)       // 0 waiting for stage F, 1 near matches, 2 long matches, 3 near matches (count)
     for (uint32_t t = 0;; t++) {
         bool fin = false;
-        while (vld(&ctl->far_done[t & (kTickets - 1)]) != t + 1) {          // (stage F has waited for the ticket and for stage L)
+        while (!bar_try(ctl->bar_far, t))                                   // (stage F has waited for the ticket and for stage L)
             if (vld(&ctl->finished) && (int)(t - vld(&ctl->t_final)) >= 0) { fin = true; break; }
-            __nanosleep(20);
-        }
         if (fin) break;
-        __threadfence_block();
         uint32_t dep = vld(&ctl->near_mask[t & (kWSlots - 1)]);
         const uint32_t is_long = vld(&ctl->near_long[t & (kWSlots - 1)]);
         const uint32_t dslot = desc_s + (t & (kWSlots - 1)) * 512u;
@@ -648,9 +656,7 @@ __device__ void wstage_near(const DecompressArgs& a, WCtl* ctl, uint32_t out_s, 
             }
             WSTAT(1)
         }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) vst(&ctl->near_next, t + 1);
+        bar_signal(ctl->bar_near, t);
     }
     WSTAT_FLUSH(a, 15, 4)
 }
@@ -665,8 +671,7 @@ __device__ void wstage_flush(const DecompressArgs& a, int w, WCtl* ctl, uint32_t
         if (!wait_ticket(ctl, t)) break;
         const WTk k = read_ticket(ctl, t);
         const uint32_t e = vld(&ctl->tend[t & (kTickets - 1)]);
-        while ((int)(vld(&ctl->near_next) - t) <= 0) __nanosleep(20);
-        __threadfence_block();
+        bar_wait(ctl->bar_near, t);
         WSTAT(0)
         const uint32_t s_pos = k.base + k.op_start;
         if (e != s_pos) {
@@ -698,6 +703,11 @@ decompress_kernel_wide(DecompressArgs a)
     uint8_t* stages = descs + kWSlots * 512;
     WCtl* ctl = reinterpret_cast<WCtl*>(stages + kWL * kWStage);
     for (uint32_t i = threadIdx.x; i < sizeof(WCtl) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ctl)[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x < kTickets) {
+        mbar_init(&ctl->bar_ticket[threadIdx.x], 1); mbar_init(&ctl->bar_lit[threadIdx.x], 1);
+        mbar_init(&ctl->bar_far[threadIdx.x], 1); mbar_init(&ctl->bar_near[threadIdx.x], 1);
+    }
     __syncthreads();
     const int warp = (int)(threadIdx.x >> 5);
     uint4* garena = a.wide_arena + (size_t)blockIdx.x * (kWideArenaPerCta / 16);
