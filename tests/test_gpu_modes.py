@@ -14,9 +14,10 @@ SUBSET = ["tests/test_gpu_fuzz.py", "tests/test_gpu_parity.py", "-k",
           "random_round_trips or echoing or split_over or generators or edge_sizes or acceleration_sweep or linked_state"]
 
 
-DECODE_SUBSET = ["tests/test_gpu_fuzz.py", "tests/test_gpu_parity.py", "-k",
+DECODE_SUBSET = ["tests/test_gpu_fuzz.py", "tests/test_gpu_parity.py", "tests/test_gpu_configs.py", "-k",
                  "handbuilt or corrupted or random_round_trips or echoing or split_over or generators or edge_sizes or "
-                 "empty_and_tiny or block_max or large_blocks or linked_state or malformed or fragmented"]
+                 "empty_and_tiny or block_max or large_blocks or linked_state or malformed or fragmented or "
+                 "config3 or config4"]       # config 3: 1 678 one-block streams = several streams per CTA in the wide kernel
 
 
 @pytest.mark.parametrize("env", [{"B200LZ4_DWIDE": "0"},        # every decode through the narrow kernel (parser + copier warp per stream)
