@@ -34,6 +34,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # before CUDA is initialised (see streamly_lz4_b200/_lib.py)
 
 BLOCK = 640000
 ACCEL = 400

@@ -8,6 +8,11 @@ from __future__ import annotations
 import ctypes
 import os
 
+# The streamed host calls want the copy streams and the kernel streams on separate hardware work queues (csrc/api.cu:
+# probe_stream_aliasing); CUDA reads this when the context is created, so ask before anything initialises CUDA.  The
+# library's own load-time constructor does the same for non-Python hosts.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200LZ4_LIB") or os.path.join(_HERE, "libb200lz4.so")   # override: A/B builds of the same ABI
 

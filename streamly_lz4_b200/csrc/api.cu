@@ -70,6 +70,9 @@ struct PinBuf {
 constexpr int kMaxChunks = 6;           // pipeline depth of the host batch calls (H2D + D2H + chunk streams must fit the
                                         // 8 hardware queues of the default CUDA_DEVICE_MAX_CONNECTIONS, else chunks serialize)
 constexpr int kKernelStreams = kMaxChunks;   // one stream per chunk: chunk kernels must be able to overlap
+constexpr int kMaxGroups = 16;          // streamed compress call: block groups (events, work counters, arrival flags)
+constexpr int kMaxSegs = 16;            // ... and segments a block is cut into on its way to / from the device
+constexpr size_t kFlagBytes = 1024 + kMaxGroups * kMaxSegs * sizeof(uint32_t);   // ctx->d_flags: see b200lz4_ctx
 
 struct b200lz4_ctx {
     int device = 0;
@@ -80,7 +83,18 @@ struct b200lz4_ctx {
     DevBuf d_src, d_slots, d_out, d_desc, d_wide;   // d_wide: descriptor rings of decompress_kernel_wide (one slice per chunk)
     PinBuf h_desc;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_k0 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+    cudaEvent_t ev_h2d[kMaxGroups] = {}, ev_k[kMaxGroups] = {}, ev_k0 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+    // streamed compress call (compress_host_streamed): per-group arrival flags + finder cycle counters in HBM, the
+    // constants the copy stream writes into the flags, and what earlier calls measured (the copy schedule is tuned by it)
+    uint32_t* d_flags = nullptr;            // [kMaxGroups] u32 flags, then at byte 64: u64 busy cycles, u64 bytes; at byte 1024:
+                                            // [kMaxGroups][kMaxSegs] u32 segment counters of the streamed decompress call
+    uint32_t* h_const = nullptr;            // pinned: h_const[i] == i
+    double est_ns_per_byte = 0;             // finder time per input byte (0 = not measured yet)
+    double est_h2d_gbs = 0;                 // H2D bandwidth of the last streamed call
+    int clock_khz = 0;
+    int streamed_calls = 0;
+    int n_kgood = -1;                       // kernel streams verified not to share a hardware queue with the copy streams
+                                            // or with each other (-1: not probed yet); they come first in kstream[]
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
     int64_t launches = 0;
     std::string err;                                // text of the last failure of a call on this ctx (any thread)
@@ -191,6 +205,309 @@ int plan_chunks(const int64_t* off, const int32_t* len, int n, const int32_t* fi
     return k;
 }
 
+// ---- hardware-queue aliasing ---------------------------------------------------
+// CUDA multiplexes streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware work queues (8 unless the variable is set before the
+// context exists; the library's load-time constructor below asks for 32).  Entries of one queue are dispatched in order, so
+// anything queued behind a kernel's same-stream successor waits for that kernel to END -- harmless for the plain pipeline,
+// fatal for the streamed call, whose kernels wait for copies that are queued later on the copy stream.  Which streams share
+// a queue is not documented, so it is MEASURED once per ctx: a kernel that spins on a flag (bounded by a timeout), a
+// successor behind it, then a write of the flag through the other stream; if the spinning kernel times out, the two
+// streams share a queue.  Kernel streams that alias the H2D stream, the D2H stream or an already accepted kernel stream are
+// replaced by fresh ones (up to 40 tries).
+__attribute__((constructor)) void ask_for_more_hardware_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+// (CUDA_MODULE_LOADING is deliberately left alone: probe_stream_aliasing loads the few kernels that matter by hand.)
+
+int streams_alias(b200lz4_ctx* c, cudaStream_t spinner, cudaStream_t other, bool other_writes_by_kernel, bool* aliased)
+{
+    uint32_t* flag = c->d_flags + 40;       // bytes 160.. of the flag block: not used by the calls themselves
+    uint32_t* result = c->d_flags + 44;
+    CU(cudaMemsetAsync(flag, 0, 32, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(launch_alias_probe(flag, result, (long long)c->clock_khz * 15, spinner));     // 15 ms
+    if (other_writes_by_kernel) CU(launch_set_flag(flag, 1u, other));
+    else CU(cudaMemcpyAsync(flag, c->h_const + 1, sizeof(uint32_t), cudaMemcpyHostToDevice, other));
+    CU(cudaStreamSynchronize(spinner));
+    CU(cudaStreamSynchronize(other));
+    uint32_t r[2] = {0, 0};
+    CU(cudaMemcpy(r, result, sizeof r, cudaMemcpyDeviceToHost));
+    *aliased = (r[0] != 1u);
+    return 0;
+}
+
+int probe_stream_aliasing(b200lz4_ctx* c)
+{
+    if (c->n_kgood >= 0) return 0;
+    // every kernel a streamed call launches is loaded NOW: a lazy first-time load in the middle of the call waits for
+    // running kernels to end, and those wait for copies the blocked host thread has not queued yet
+    CU(preload_compress_kernels());
+    CU(preload_compact_kernels());
+    {   // ... including whatever the runtime itself uses for memset and small copies: run each once
+        CU(cudaMemsetAsync(c->d_flags, 0, kFlagBytes, c->stream));
+        CU(cudaMemcpyAsync(c->d_flags + 48, c->h_const + 1, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CU(launch_set_flag(c->d_flags + 48, 0u, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    std::vector<cudaStream_t> good, rejected;
+    int next_existing = 0, tries = 0, rc;
+    while ((int)good.size() < kKernelStreams && tries < 40) {
+        cudaStream_t cand;
+        if (next_existing < kKernelStreams) cand = c->kstream[next_existing++];
+        else CU(cudaStreamCreateWithFlags(&cand, cudaStreamNonBlocking));
+        tries++;
+        bool bad = false;
+        if ((rc = streams_alias(c, cand, c->stream, false, &bad))) return rc;
+        if (!bad && (rc = streams_alias(c, cand, c->dstream, false, &bad))) return rc;
+        for (size_t j = 0; j < good.size() && !bad; j++) if ((rc = streams_alias(c, good[j], cand, true, &bad))) return rc;
+        (bad ? rejected : good).push_back(cand);
+    }
+    while (next_existing < kKernelStreams) rejected.push_back(c->kstream[next_existing++]);
+    c->n_kgood = (int)good.size();
+    int k = 0;
+    for (cudaStream_t x : good) c->kstream[k++] = x;
+    for (cudaStream_t x : rejected) { if (k < kKernelStreams) c->kstream[k++] = x; else cudaStreamDestroy(x); }
+    if (getenv("B200LZ4_DEBUG")) fprintf(stderr, "[b200lz4] hardware queues: %d of %d kernel streams independent of the copy streams after %d tries\n", c->n_kgood, kKernelStreams, tries);
+    return 0;
+}
+
+// One segment of every block of a group: `rows` ranges of `width` bytes at constant pitches.  Either one pitched copy
+// (cudaMemcpy2DAsync) or one batch of plain 1-D copies (cudaMemcpyBatchAsync, CUDA 12.8+): the copy engine moves a pitched
+// copy row by row, which measured 15 % slower than plain copies while the opposite direction is busy.
+int copy_rows(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t spitch, size_t width, size_t rows, cudaMemcpyKind kind,
+              cudaStream_t st, bool batch)
+{
+    if (rows == 0 || width == 0) return 0;
+    if (!batch || rows == 1) {
+        if (rows == 1) CU(cudaMemcpyAsync(dst, src, width, kind, st));
+        else CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st));
+        return 0;
+    }
+    thread_local std::vector<void*> d, s2;
+    thread_local std::vector<size_t> sz;
+    d.resize(rows); s2.resize(rows); sz.assign(rows, width);
+    for (size_t r = 0; r < rows; r++) { d[r] = dst + r * dpitch; s2[r] = const_cast<uint8_t*>(src) + r * spitch; }
+    cudaMemcpyAttributes at{};
+    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t idx = 0, fail_idx = 0;
+    CU(cudaMemcpyBatchAsync(d.data(), s2.data(), sz.data(), rows, &at, &idx, 1, &fail_idx, st));
+    return 0;
+}
+inline bool stream_copy_batch() { const char* e = getenv("B200LZ4_STREAM_COPY"); return e ? e[0] == 'b' : false; }
+
+// ---- streamed compress call ---------------------------------------------------
+// A batch of equally long independent blocks at a constant pitch (what compressChunks over fixed-size reads produces)
+// does not have to arrive block by block.  The end of the plain pipeline above is "last byte lands + one BLOCK latency"
+// (a 640 000-byte block keeps one finder busy for ~7 ms, a third of the whole transfer).  Here blocks are cut into S
+// segments and block groups into 2-D copies (one segment of every block of a group per copy), each followed by a 4-byte
+// copy that bumps the group's arrival flag; the group's kernel is launched as soon as its FIRST segment has landed and
+// its finders wait for later segments only if they get there before the data (compress.cu: kStreamed).  Pieces are sent
+// in deadline order, key(g, s) = g + s * w: w = 0 is the plain block order, a large w sends segment 0 of every block
+// first.  w is chosen so that a group's segments arrive at the pace its finders consume them, from what the previous
+// streamed call on this ctx measured (finder cycles per byte, H2D rate); then the end of the call is "last byte lands +
+// one SEGMENT latency + the last group's D2H".  The device layout is private to the call (128-byte aligned block starts,
+// 128 bytes of gap), so no L1 sector is read before it is complete.
+struct StreamShape { int L; int64_t P; bool ok; };
+constexpr double kStreamSpread = 1.5;    // measured: a little later is better than a little early (the D2H copies of finished groups
+                                        // share the link, and a starved finder only waits while an early piece delays everyone else's)
+constexpr int kStreamedGaveUp = -1000;  // internal: compress_host retries through the plain pipeline
+
+StreamShape streamed_shape(const int64_t* off, const int32_t* len, int n, const int32_t* stream_first, const int32_t* block_cap)
+{
+    StreamShape r{0, 0, false};
+    static const bool off_env = getenv("B200LZ4_NO_STREAMED") != nullptr;
+    if (off_env || stream_first || block_cap || n < 96) return r;
+    const int L = len[0];
+    if (L < 65536 || (int64_t)L * n < (int64_t(96) << 20)) return r;
+    const int64_t P = off[1] - off[0];
+    if (P < L) return r;
+    for (int i = 0; i < n; i++) {
+        if (off[i] != off[0] + P * i) return r;
+        if (i < n - 1 ? len[i] != L : (len[i] <= 0 || len[i] > L)) return r;
+    }
+    r.L = L; r.P = P; r.ok = true;
+    return r;
+}
+
+int compress_host_streamed(b200lz4_ctx* c, const void* src, const int64_t* src_off, const int32_t* src_len, int n,
+                           const StreamShape& shp, int accel, int header,
+                           void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
+{
+    int rc;
+    const int L = shp.L;
+    const int nks = c->n_kgood;             // kernel streams that cannot block the copy stream (>= 2, checked by the caller)
+    const int64_t DP = ((int64_t)L + 127) / 128 * 128 + 128;       // device pitch
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) total += src_len[i];
+
+    // ---- schedule parameters
+    const char* env_w = getenv("B200LZ4_STREAM_W");      // measurement overrides (read per call)
+    const char* env_g = getenv("B200LZ4_STREAM_G");
+    const char* env_s = getenv("B200LZ4_STREAM_S");
+    const char* env_f = getenv("B200LZ4_STREAM_FLAG");
+    const bool flag_by_kernel = env_f && env_f[0] == 'k';
+    const bool batch_copies = stream_copy_batch();
+    const double ns_per_byte = c->est_ns_per_byte > 0 ? c->est_ns_per_byte : 12.0;       // first call: ~85 MB/s per finder
+    const double h2d_gbs = c->est_h2d_gbs > 0 ? c->est_h2d_gbs : 50.0;
+    const double t_block_ms = ns_per_byte * 1.1 * L * 1e-6, t_h2d_ms = (double)total / (h2d_gbs * 1e6);
+    const double rho = t_block_ms / t_h2d_ms;
+    int G = env_g ? atoi(env_g) : (rho <= 0.45 ? 2 * nks : nks);        // a group runs behind group g - nks on its stream
+    if (G < 1) G = 1;
+    if (G > kMaxGroups) G = kMaxGroups;
+    int S = env_s ? atoi(env_s) : 8;
+    if (S < 1) S = 1;
+    if (S > kMaxSegs) S = kMaxSegs;
+    const int seg = (int)((((int64_t)L + S - 1) / S + 127) / 128 * 128);
+    S = (L + seg - 1) / seg;
+    const int per_group = (n + G - 1) / G;
+    G = (n + per_group - 1) / per_group;
+    // a group's S pieces are (S - 1) * w key units apart, the whole schedule spans (G - 1) + (S - 1) * w units in t_h2d:
+    // the last piece of a group should land when its finders get there, (S - 1) / S of a block time after the first
+    double w = (double)G;
+    if (S - rho * (S - 1) > 0.01) w = kStreamSpread * rho * (G - 1) / (S - rho * (S - 1));
+    if (env_w) w = atof(env_w);
+    if (w > G) w = G;
+
+    // ---- descriptor block (device offsets are the private layout)
+    Carver cv;
+    const size_t o_src_off = cv.take(sizeof(int64_t) * n);
+    const size_t o_slot_off = cv.take(sizeof(int64_t) * n);
+    const size_t o_src_len = cv.take(sizeof(int32_t) * n);
+    const size_t o_upload_end = cv.off;
+    const size_t o_out_len = cv.take(sizeof(int32_t) * n);
+    const size_t o_out_off = cv.take(sizeof(int64_t) * (n + G));
+    const size_t desc_bytes = cv.off;
+    if ((rc = c->h_desc.ensure(desc_bytes))) return rc;
+    if ((rc = c->d_desc.ensure(desc_bytes))) return rc;
+    uint8_t* hd = static_cast<uint8_t*>(c->h_desc.p);
+    uint8_t* dd = static_cast<uint8_t*>(c->d_desc.p);
+    int64_t* h_src_off = reinterpret_cast<int64_t*>(hd + o_src_off);
+    int64_t* h_slot_off = reinterpret_cast<int64_t*>(hd + o_slot_off);
+    memcpy(hd + o_src_len, src_len, sizeof(int32_t) * n);
+    int64_t slots_total = 0;
+    for (int i = 0; i < n; i++) {
+        h_src_off[i] = DP * i;
+        h_slot_off[i] = slots_total;
+        slots_total += align16((int64_t)bound_of(src_len[i]) + header + 16);
+    }
+    if ((rc = c->d_src.ensure((size_t)(DP * n) + 256))) return rc;
+    if ((rc = c->d_slots.ensure((size_t)slots_total + 64))) return rc;
+    if ((rc = c->d_out.ensure((size_t)slots_total + 64))) return rc;
+    const uint8_t* hsrc = static_cast<const uint8_t*>(src);
+    uint8_t* d_src = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(c->d_src.p) + 127) & ~uintptr_t(127));
+    uint8_t* d_slots = static_cast<uint8_t*>(c->d_slots.p);
+    uint8_t* d_out = static_cast<uint8_t*>(c->d_out.p);
+    int64_t* d_out_off = reinterpret_cast<int64_t*>(dd + o_out_off);
+    int32_t* d_out_len = reinterpret_cast<int32_t*>(dd + o_out_len);
+    unsigned long long* d_busy = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(c->d_flags) + 64);
+
+    // ---- pieces in deadline order
+    struct Piece { int g, s; double key; };
+    std::vector<Piece> pieces;
+    pieces.reserve((size_t)G * S);
+    for (int g = 0; g < G; g++) for (int s2 = 0; s2 < S; s2++) pieces.push_back({g, s2, g + s2 * w});
+    std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.key < y.key; });
+
+    cudaStream_t st = c->stream;
+    CU(cudaEventRecord(c->ev[0], st));
+    CU(cudaMemsetAsync(c->d_flags, 0, 256, st));
+    CU(cudaMemcpyAsync(dd, hd, o_upload_end, cudaMemcpyHostToDevice, st));
+    bool first_kernel = true;
+    for (const Piece& pc : pieces) {
+        const int b0 = pc.g * per_group, b1 = std::min(n, b0 + per_group);
+        const int lo = pc.s * seg, width = std::min(seg, L - lo);
+        int rows = b1 - b0;
+        if (b1 == n && src_len[n - 1] < L) {        // the batch's last block may be shorter: its share of the segment goes separately
+            rows--;
+            const int wl = std::min(width, src_len[n - 1] - lo);
+            if (wl > 0) CU(cudaMemcpyAsync(d_src + DP * (n - 1) + lo, hsrc + src_off[n - 1] + lo, (size_t)wl, cudaMemcpyHostToDevice, st));
+        }
+        if (rows > 0 && (rc = copy_rows(d_src + DP * b0 + lo, (size_t)DP, hsrc + src_off[b0] + lo, (size_t)shp.P, (size_t)width, (size_t)rows,
+                                        cudaMemcpyHostToDevice, st, batch_copies))) return rc;
+        if (flag_by_kernel) CU(launch_set_flag(c->d_flags + pc.g, (uint32_t)(pc.s + 1), st));
+        else CU(cudaMemcpyAsync(c->d_flags + pc.g, c->h_const + (pc.s + 1), sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (pc.s != 0) continue;
+        // first segment of the group is on its way: queue the group's kernels behind it
+        CU(cudaEventRecord(c->ev_h2d[pc.g], st));
+        cudaStream_t ks = c->kstream[pc.g % nks];
+        CU(cudaStreamWaitEvent(ks, c->ev_h2d[pc.g], 0));
+        if (first_kernel) { CU(cudaEventRecord(c->ev_k0, ks)); first_kernel = false; }
+        CompressArgs a{};
+        a.src = d_src;
+        a.src_off = reinterpret_cast<const int64_t*>(dd + o_src_off);
+        a.src_len = reinterpret_cast<const int32_t*>(dd + o_src_len);
+        a.n_blocks = n;
+        a.first_block = b0;
+        a.n_streams = b1 - b0;
+        a.dst = d_slots;
+        a.dst_off = reinterpret_cast<const int64_t*>(dd + o_slot_off);
+        a.out_len = d_out_len;
+        a.accel = accel; a.header = header; a.scratch = c->scratch + pc.g;
+        a.arrived = c->d_flags + pc.g; a.seg_bytes = seg; a.busy_cycles = d_busy;
+        CU(launch_compress(a, ks));
+        CompactArgs cg{d_slots, a.dst_off + b0, d_out_len + b0, b1 - b0, header, d_out + h_slot_off[b0], d_out_off + b0 + pc.g,
+                       reinterpret_cast<int64_t*>(hd + o_out_off) + b0 + pc.g, reinterpret_cast<int32_t*>(hd + o_out_len) + b0};
+        CU(launch_compact(cg, ks));
+        c->launches += kernel_launches_per_compress() + kernel_launches_per_compact();
+        CU(cudaEventRecord(c->ev_k[pc.g], ks));
+    }
+    CU(cudaEventRecord(c->ev[1], st));
+    const bool dbg = getenv("B200LZ4_DEBUG") != nullptr;
+    if (dbg) { fprintf(stderr, "[b200lz4] streamed: %zu pieces queued (G %d S %d seg %d w %.3f)\n", pieces.size(), G, S, seg, w); fflush(stderr); }
+
+    // drain: as each group's sizes arrive, send its compacted bytes home
+    const int32_t* h_out_len = reinterpret_cast<const int32_t*>(hd + o_out_len);
+    const int64_t* h_out_off = reinterpret_cast<const int64_t*>(hd + o_out_off);
+    int64_t base = 0;
+    int result = 0;
+    CU(cudaEventRecord(c->ev_d0, c->dstream));
+    for (int g = 0; g < G; g++) {
+        const int b0 = g * per_group, b1 = std::min(n, b0 + per_group);
+        CU(cudaEventSynchronize(c->ev_k[g]));
+        if (dbg) { fprintf(stderr, "[b200lz4] streamed: group %d done\n", g); fflush(stderr); }
+        const int nk = b1 - b0;
+        const int64_t* off_k = h_out_off + b0 + g;
+        const int64_t total_k = off_k[nk];
+        for (int i = 0; i < nk; i++) dst_off[b0 + i] = base + off_k[i];
+        if (base + total_k > dst_cap) { result = fail(B200LZ4_E_NOMEM, "dst_cap too small"); break; }
+        if (total_k) CU(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + base, d_out + h_slot_off[b0], (size_t)total_k,
+                                        cudaMemcpyDeviceToHost, c->dstream));
+        base += total_k;
+    }
+    dst_off[n] = base;
+    CU(cudaEventRecord(c->ev_d1, c->dstream));
+    if ((rc = sync_all(c))) return rc;
+    if (result) return result;
+    memcpy(out_len, h_out_len, sizeof(int32_t) * n);
+    cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->t_kernel, c->ev_k0, c->ev_k[G - 1]);
+    cudaEventElapsedTime(&c->t_d2h, c->ev_d0, c->ev_d1);
+    // what this call measured tunes the next one's schedule
+    unsigned long long busy[3] = {0, 0, 0};
+    CU(cudaMemcpy(busy, d_busy, sizeof busy, cudaMemcpyDeviceToHost));
+    if (busy[2]) { fail(B200LZ4_E_CUDA, "streamed compress: " + std::to_string(busy[2]) + " blocks gave up waiting for their input segments"); return kStreamedGaveUp; }
+    if (busy[1] && c->clock_khz > 0) {
+        const double ns = (double)busy[0] / (double)busy[1] / ((double)c->clock_khz * 1e-6);
+        c->est_ns_per_byte = c->est_ns_per_byte > 0 ? 0.5 * c->est_ns_per_byte + 0.5 * ns : ns;
+    }
+    if (c->t_h2d > 0) {
+        const double gbs = (double)total / ((double)c->t_h2d * 1e6);
+        c->est_h2d_gbs = c->est_h2d_gbs > 0 ? 0.5 * c->est_h2d_gbs + 0.5 * gbs : gbs;
+    }
+    c->streamed_calls++;
+    if (getenv("B200LZ4_DEBUG")) {
+        fprintf(stderr, "[b200lz4] streamed: G %d S %d seg %d w %.3f rho %.3f  est %.2f ns/B  h2d %.1f GB/s\n", G, S, seg, w, rho, c->est_ns_per_byte, c->est_h2d_gbs);
+        float t = 0;
+        for (int g = 0; g < G; g++) {
+            float x = 0, y = 0;
+            cudaEventElapsedTime(&x, c->ev[0], c->ev_h2d[g]); cudaEventElapsedTime(&y, c->ev[0], c->ev_k[g]);
+            fprintf(stderr, "[b200lz4] group %d: first segment landed %.2f  kernels done %.2f\n", g, x, y);
+        }
+        cudaEventElapsedTime(&t, c->ev[0], c->ev[1]); fprintf(stderr, "[b200lz4] h2d done %.2f\n", t);
+        cudaEventElapsedTime(&t, c->ev[0], c->ev_d1); fprintf(stderr, "[b200lz4] d2h done %.2f\n", t);
+    }
+    for (int i = 0; i < n; i++) if (out_len[i] <= 0) return fail(B200LZ4_E_BLOCK, "block " + std::to_string(i) + " failed to compress");
+    return 0;
+}
+
 int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
                   const int64_t* src_off, const int32_t* src_len, int n,
                   const int32_t* stream_first, int n_streams, b200lz4_cstream* const* streams,
@@ -208,6 +525,20 @@ int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     if ((rc = check_streams(stream_first, n_streams, n))) return rc;
     CU(cudaSetDevice(c->device));
     const int ns = stream_first ? n_streams : n;
+    if (!streams) {
+        const StreamShape shp = streamed_shape(src_off, src_len, n, stream_first, block_cap);
+        if (shp.ok) {
+            if ((rc = probe_stream_aliasing(c))) return rc;
+            if (c->n_kgood >= 2) {
+                rc = compress_host_streamed(c, src, src_off, src_len, n, shp, accel, header, dst, dst_cap, dst_off, out_len);
+                if (rc != kStreamedGaveUp) return rc;
+                // finders gave up waiting for their input (should not happen on verified streams): never again on this
+                // ctx, and this batch goes through the plain pipeline
+                c->n_kgood = 0;
+                if (getenv("B200LZ4_DEBUG")) fprintf(stderr, "[b200lz4] streamed call gave up (%s): plain pipeline from now on\n", g_err.c_str());
+            }
+        }
+    }
 
     // stream state: make sure each persistent stream can keep its last array
     if (streams) {
@@ -345,6 +676,9 @@ int compress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
 inline int32_t le32(const uint8_t* p)
 { return (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24)); }
 
+int decompress_host_streamed(b200lz4_ctx* c, const void* src, const int64_t* src_off, const int32_t* src_len, int n,
+                             int L, int cap_last, void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len);
+
 int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
                     const int64_t* src_off, const int32_t* src_len, int n,
                     const int32_t* stream_first, int n_streams, b200lz4_dstream* const* streams,
@@ -365,6 +699,19 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     const int ns = stream_first ? n_streams : n;
     if (streams) for (int s = 0; s < n_streams; s++)
         if (!streams[s] || streams[s]->ctx != c) return fail(B200LZ4_E_ARG, "stream handle belongs to another ctx");
+    const uint8_t* hsrc = static_cast<const uint8_t*>(src);
+    // equally large independent blocks with their size in the header: the output leaves segment by segment
+    static const bool no_streamed = getenv("B200LZ4_NO_STREAMED") != nullptr;
+    if (!no_streamed && header == 8 && !stream_first && !streams && n >= 96 && src_len[0] >= 8) {
+        const int L = le32(hsrc + src_off[0] + 4);
+        bool ok = L >= 65536 && (int64_t)L * n >= (int64_t(96) << 20);
+        int cap_last = 0;
+        for (int i = 0; i < n && ok; i++) {
+            const int cap = src_len[i] >= 8 ? le32(hsrc + src_off[i] + 4) : -1;
+            if (i < n - 1) ok = (cap == L); else { ok = (cap > 0 && cap <= L); cap_last = cap; }
+        }
+        if (ok) return decompress_host_streamed(c, src, src_off, src_len, n, L, cap_last, dst, dst_cap, dst_off, out_len);
+    }
     Chunk chunks[kMaxChunks];
     const int nchunks = plan_chunks(src_off, src_len, n, stream_first, ns, chunks);
 
@@ -388,7 +735,6 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     memcpy(hd + o_src_off, src_off, sizeof(int64_t) * n);
     memcpy(hd + o_src_len, src_len, sizeof(int32_t) * n);
     // capacities: the header's uncompLen (BlockHasSize) or the configured maximum (LZ4.hs:189-198)
-    const uint8_t* hsrc = static_cast<const uint8_t*>(src);
     int64_t slots_total = 0;
     for (int i = 0; i < n; i++) {
         int cap = max_block;
@@ -499,6 +845,183 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     return 0;
 }
 
+// ---- streamed decompress call --------------------------------------------------
+// The mirror image of compress_host_streamed for the OUTPUT side: decompression of equally large independent blocks is
+// bound by the D2H copy (1.40 x the bytes of the H2D copy on config 2), and in the plain pipeline the first byte cannot
+// leave before a whole chunk has arrived AND one block latency has passed.  Here every group's kernel counts, per segment of
+// the (equal) block capacity, the blocks whose flushed output has passed it (decompress.cu: kPublish); the last one raises
+// a flag in page-locked host memory, the calling thread polls the flags and queues that segment of every block of the
+// group as one 2-D D2H copy.  The copy engine then runs from "first group landed + one SEGMENT latency" to the end.
+int decompress_host_streamed(b200lz4_ctx* c, const void* src, const int64_t* src_off, const int32_t* src_len, int n,
+                             int L, int cap_last, void* dst, int64_t dst_cap, int64_t* dst_off, int32_t* out_len)
+{
+    int rc;
+    const int header = 8;
+    const int64_t out_total = (int64_t)L * (n - 1) + cap_last;
+    if (out_total > dst_cap) return fail(B200LZ4_E_NOMEM, "dst_cap too small: need " + std::to_string(out_total));
+    const char* env_g = getenv("B200LZ4_STREAM_G");
+    const char* env_s = getenv("B200LZ4_STREAM_S");
+    int G = env_g ? atoi(env_g) : 12;
+    if (G < 1) G = 1;
+    if (G > kMaxGroups) G = kMaxGroups;
+    int S = env_s ? atoi(env_s) : 8;
+    if (S < 1) S = 1;
+    if (S > kMaxSegs) S = kMaxSegs;
+    const int seg = (int)((((int64_t)L + S - 1) / S + 127) / 128 * 128);
+    S = (L + seg - 1) / seg;
+    const int per_group = (n + G - 1) / G;
+    G = (n + per_group - 1) / per_group;
+    if ((rc = probe_stream_aliasing(c))) return rc;     // nothing can deadlock here, but kernels queued behind another group's would start late
+    const int nks = c->n_kgood >= 2 ? c->n_kgood : kKernelStreams;
+
+    Carver cv;
+    const size_t o_src_off = cv.take(sizeof(int64_t) * n);
+    const size_t o_slot_off = cv.take(sizeof(int64_t) * n);
+    const size_t o_src_len = cv.take(sizeof(int32_t) * n);
+    const size_t o_cap = cv.take(sizeof(int32_t) * n);
+    const size_t o_upload_end = cv.off;
+    const size_t o_out_len = cv.take(sizeof(int32_t) * n);
+    const size_t o_ready = cv.take(sizeof(uint32_t) * kMaxGroups * kMaxSegs);
+    const size_t desc_bytes = cv.off;
+    if ((rc = c->h_desc.ensure(desc_bytes))) return rc;
+    if ((rc = c->d_desc.ensure(desc_bytes))) return rc;
+    uint8_t* hd = static_cast<uint8_t*>(c->h_desc.p);
+    uint8_t* dd = static_cast<uint8_t*>(c->d_desc.p);
+    int64_t* h_slot_off = reinterpret_cast<int64_t*>(hd + o_slot_off);
+    int32_t* h_cap = reinterpret_cast<int32_t*>(hd + o_cap);
+    volatile uint32_t* ready = reinterpret_cast<volatile uint32_t*>(hd + o_ready);
+    memcpy(hd + o_src_off, src_off, sizeof(int64_t) * n);
+    memcpy(hd + o_src_len, src_len, sizeof(int32_t) * n);
+    int64_t src_hi = 0;
+    for (int i = 0; i < n; i++) {
+        h_cap[i] = i < n - 1 ? L : cap_last;
+        h_slot_off[i] = (int64_t)L * i;
+        dst_off[i] = (int64_t)L * i;
+        src_hi = std::max(src_hi, src_off[i] + (int64_t)src_len[i]);
+    }
+    dst_off[n] = out_total;
+    for (int i = 0; i < kMaxGroups * kMaxSegs; i++) ready[i] = 0;
+    if ((rc = c->d_src.ensure((size_t)src_hi + 64))) return rc;
+    if ((rc = c->d_slots.ensure((size_t)out_total + 64))) return rc;
+    const uint8_t* hsrc = static_cast<const uint8_t*>(src);
+    uint8_t* d_src = static_cast<uint8_t*>(c->d_src.p);
+    uint8_t* d_slots = static_cast<uint8_t*>(c->d_slots.p);
+    uint32_t* d_counts = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(c->d_flags) + 1024);
+
+    cudaStream_t st = c->stream;
+    CU(cudaEventRecord(c->ev[0], st));
+    CU(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * kMaxGroups * kMaxSegs, st));
+    CU(cudaMemcpyAsync(dd, hd, o_upload_end, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->ev_d0, c->dstream));
+    for (int g = 0; g < G; g++) {
+        const int b0 = g * per_group, b1 = std::min(n, b0 + per_group);
+        int64_t lo = INT64_MAX, hi = 0;
+        for (int i = b0; i < b1; i++) { lo = std::min(lo, src_off[i]); hi = std::max(hi, src_off[i] + (int64_t)src_len[i]); }
+        if (hi > lo) CU(cudaMemcpyAsync(d_src + lo, hsrc + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->ev_h2d[g], st));
+        cudaStream_t ks = c->kstream[g % nks];
+        CU(cudaStreamWaitEvent(ks, c->ev_h2d[g], 0));
+        if (g == 0) CU(cudaEventRecord(c->ev_k0, ks));
+        DecompressArgs a{};
+        a.src = d_src;
+        a.src_off = reinterpret_cast<const int64_t*>(dd + o_src_off);
+        a.src_len = reinterpret_cast<const int32_t*>(dd + o_src_len);
+        a.n_blocks = n;
+        a.first_block = b0;
+        a.n_streams = b1 - b0;
+        a.dst = d_slots;
+        a.dst_off = reinterpret_cast<const int64_t*>(dd + o_slot_off);
+        a.dst_cap = reinterpret_cast<const int32_t*>(dd + o_cap);
+        a.out_len = reinterpret_cast<int32_t*>(hd + o_out_len);     // page-locked, device-visible: no small D2H copies that would queue behind the pieces
+        a.header = header; a.max_block = 0; a.scratch = c->scratch + g;
+        a.seg_count = d_counts + g * kMaxSegs;
+        a.host_ready = reinterpret_cast<uint32_t*>(hd + o_ready) + g * kMaxSegs;
+        a.seg_bytes = seg; a.n_segs = S;
+        CU(launch_decompress(a, ks));
+        c->launches += kernel_launches_per_decompress();
+        CU(cudaEventRecord(c->ev_k[g], ks));
+    }
+    CU(cudaEventRecord(c->ev[1], st));
+
+    // drain: queue every (group, segment) piece as soon as its flag is up
+    int next_s[kMaxGroups] = {0};
+    int remaining = G * S;
+    uint8_t* hdst = static_cast<uint8_t*>(dst);
+    const bool dbg = getenv("B200LZ4_DEBUG") != nullptr;
+    const bool batch_copies = stream_copy_batch();
+    struct PieceLog { int g, s; double issued_ms; cudaEvent_t done; };
+    std::vector<PieceLog> plog;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    auto send = [&](int g, int sgm) -> int {
+        const int b0 = g * per_group, b1 = std::min(n, b0 + per_group);
+        const int lo = sgm * seg, width = std::min(seg, L - lo);
+        int rows = b1 - b0;
+        if (b1 == n && cap_last < L) {
+            rows--;
+            const int wl = std::min(width, cap_last - lo);
+            if (wl > 0) CU(cudaMemcpyAsync(hdst + (int64_t)L * (n - 1) + lo, d_slots + (int64_t)L * (n - 1) + lo, (size_t)wl, cudaMemcpyDeviceToHost, c->dstream));
+        }
+        if (rows > 0) return copy_rows(hdst + (int64_t)L * b0 + lo, (size_t)L, d_slots + (int64_t)L * b0 + lo, (size_t)L, (size_t)width, (size_t)rows,
+                                       cudaMemcpyDeviceToHost, c->dstream, batch_copies);
+        return 0;
+    };
+    long spins = 0;
+    while (remaining) {
+        bool any = false;
+        for (int g = 0; g < G; g++) {
+            while (next_s[g] < S && ready[g * kMaxSegs + next_s[g]]) {
+                if ((rc = send(g, next_s[g]))) return rc;
+                if (dbg) {
+                    PieceLog pl{g, next_s[g], std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(), nullptr};
+                    cudaEventCreate(&pl.done); cudaEventRecord(pl.done, c->dstream);
+                    plog.push_back(pl);
+                }
+                next_s[g]++; remaining--; any = true;
+            }
+        }
+        if (any) { spins = 0; continue; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if (++spins % 4096 == 0) {          // a faulted or finished kernel must not leave this loop spinning
+            bool all_done = true;
+            for (int g = 0; g < G; g++) {
+                const cudaError_t q = cudaEventQuery(c->ev_k[g]);
+                if (q == cudaErrorNotReady) { all_done = false; break; }
+                if (q != cudaSuccess) return fail_cuda(q, "streamed decompress");
+            }
+            if (all_done) {                 // every block has ended, so every flag is up: one last look
+                bool missing = false;
+                for (int g = 0; g < G; g++) for (int k = next_s[g]; k < S; k++) if (!ready[g * kMaxSegs + k]) missing = true;
+                if (missing) return fail(B200LZ4_E_CUDA, "streamed decompress: kernels ended without raising every segment flag");
+            }
+        }
+    }
+    CU(cudaEventRecord(c->ev_d1, c->dstream));
+    if ((rc = sync_all(c))) return rc;
+    cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->t_kernel, c->ev_k0, c->ev_k[G - 1]);
+    cudaEventElapsedTime(&c->t_d2h, c->ev_d0, c->ev_d1);
+    memcpy(out_len, hd + o_out_len, sizeof(int32_t) * n);
+    if (getenv("B200LZ4_DEBUG")) {
+        fprintf(stderr, "[b200lz4] streamed decompress: G %d S %d seg %d\n", G, S, seg);
+        float t = 0;
+        for (int g = 0; g < G; g++) {
+            float x = 0, y = 0;
+            cudaEventElapsedTime(&x, c->ev[0], c->ev_h2d[g]); cudaEventElapsedTime(&y, c->ev[0], c->ev_k[g]);
+            fprintf(stderr, "[b200lz4] group %d: input landed %.2f  kernel done %.2f\n", g, x, y);
+        }
+        cudaEventElapsedTime(&t, c->ev[0], c->ev_d1); fprintf(stderr, "[b200lz4] d2h done %.2f\n", t);
+        for (auto& pl : plog) {     // (host time counts from the moment the drain loop started)
+            float x = 0; cudaEventElapsedTime(&x, c->ev[0], pl.done);
+            fprintf(stderr, "[b200lz4] piece g%d s%d: queued at host +%.2f ms, copied by %.2f\n", pl.g, pl.s, pl.issued_ms, x);
+            cudaEventDestroy(pl.done);
+        }
+    }
+    for (int i = 0; i < n; i++) if (out_len[i] < 0) return fail(B200LZ4_E_BLOCK, "block " + std::to_string(i) + " failed to decompress");
+    return 0;
+}
+
 }  // namespace
 
 // ============================================================== C ABI ====
@@ -539,10 +1062,15 @@ int b200lz4_ctx_create(int device, b200lz4_ctx** out)
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < kKernelStreams && e2 == cudaSuccess; i++) e2 = cudaStreamCreateWithFlags(&c->kstream[i], cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->dstream, cudaStreamNonBlocking);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(&c->scratch, sizeof(Scratch) * kMaxChunks);
-    if (e2 == cudaSuccess) e2 = cudaMemset(c->scratch, 0, sizeof(Scratch) * kMaxChunks);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&c->scratch, sizeof(Scratch) * kMaxGroups);
+    if (e2 == cudaSuccess) e2 = cudaMemset(c->scratch, 0, sizeof(Scratch) * kMaxGroups);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_flags, kFlagBytes);
+    if (e2 == cudaSuccess) e2 = cudaMemset(c->d_flags, 0, kFlagBytes);
+    if (e2 == cudaSuccess) e2 = cudaHostAlloc(reinterpret_cast<void**>(&c->h_const), 64 * sizeof(uint32_t), cudaHostAllocPortable);
+    if (e2 == cudaSuccess) for (uint32_t i = 0; i < 64; i++) c->h_const[i] = i;
+    if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device);
     for (int i = 0; i < 4 && e2 == cudaSuccess; i++) e2 = cudaEventCreate(&c->ev[i]);
-    for (int i = 0; i < kMaxChunks && e2 == cudaSuccess; i++) {
+    for (int i = 0; i < kMaxGroups && e2 == cudaSuccess; i++) {
         e2 = cudaEventCreate(&c->ev_h2d[i]);
         if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev_k[i]);
     }
@@ -561,6 +1089,8 @@ void b200lz4_ctx_destroy(b200lz4_ctx* c)
     cudaDeviceSynchronize();
     c->d_src.release(); c->d_slots.release(); c->d_out.release(); c->d_desc.release(); c->d_wide.release(); c->h_desc.release();
     if (c->scratch) cudaFree(c->scratch);
+    if (c->d_flags) cudaFree(c->d_flags);
+    if (c->h_const) cudaFreeHost(c->h_const);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_k) if (e) cudaEventDestroy(e);

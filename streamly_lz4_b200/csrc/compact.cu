@@ -125,6 +125,16 @@ cudaError_t launch_compact(const CompactArgs& a, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+// Loads the compaction kernels now (CUDA loads a kernel lazily at its first launch, which can wait for running kernels
+// to end -- the streamed call must never launch anything for the first time while its finders wait for input).
+cudaError_t preload_compact_kernels()
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, scan_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, gather_kernel);
+    return e;
+}
+
 int kernel_launches_per_compress() { return 1; }
 int kernel_launches_per_decompress() { return 1; }
 int kernel_launches_per_compact() { return 2; }

@@ -205,6 +205,9 @@ struct BlockIn {
     // position of contiguously loaded data, and whether both mean anything
     uint32_t w_end, w_lo; bool w_ok;
     uint32_t tbase;             // compact table: stream position of rel == 1 (carried from block to block)
+    // streamed launches (the block is still arriving over PCIe, see CompressArgs::arrived): flag word, segment size,
+    // cycles this finder spent waiting for data
+    const uint32_t* arrived; int seg; long long stall; bool timed_out;
 };
 
 // Producer side of the queue (finder warp).  The buffer being filled is always already acquired.
@@ -253,7 +256,16 @@ __device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t mask, uint32_t b
 // tbase - 1, which the distance test rejects by itself.
 constexpr uint32_t kEpoch = 65536u, kRelMax = 2 * kEpoch - 1;       // rel in [1, 131071]
 
-template <bool kWide, bool kCompact>
+// STREAMED launches (kStreamed): the block's bytes land in HBM segment by segment while the finder runs.  `avail` is the
+// number of leading bytes of the block that have arrived (a multiple of 128 or n; block starts are 128-byte aligned, so
+// no 32-byte L1 sector is ever read before it is complete); every read AHEAD of ip -- ring fills, L2 prefetches, probe
+// windows, forward counts -- first makes sure the bytes it touches lie below it (wait_for polls the flag word the
+// copy stream bumps after each segment).  Reads at or behind ip need no check.
+constexpr long long kArrivalTimeoutCycles = 2000000000LL;        // ~1 s at 2 GHz
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{ uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+template <bool kWide, bool kCompact, bool kStreamed>
 __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, const uint32_t hash_s, Producer& out,
                            const uint32_t off0, const uint32_t step0, const uint32_t off1, const uint32_t step1)
 {
@@ -269,6 +281,36 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
     const uint32_t table_s = smem_u32(table);
     int anchor = 0;
     if (kWide && n < kMinLength) in.w_ok = false;       // nothing of a tiny array reaches the ring
+    int avail = kStreamed ? 0 : n;
+    auto wait_for = [&](long long upto) {               // block until bytes [0, min(upto, n)) of the block have arrived
+        if (!kStreamed) return;
+        const int want = upto < (long long)n ? (int)upto : n;
+        if (want <= avail) return;
+        const long long t0 = clock64();
+        for (;;) {
+            const long long got = (long long)ld_acquire_sys(in.arrived) * in.seg;
+            avail = got < (long long)n ? (int)got : n;
+            if (want <= avail) break;
+            if (clock64() - t0 > kArrivalTimeoutCycles) {       // the copy stream died under us: do not spin forever, let the host fail the call
+                in.timed_out = true; avail = n;
+                break;
+            }
+            __nanosleep(2000);
+        }
+        in.stall += clock64() - t0;
+    };
+    // forward count whose first operand runs ahead of ip: a = src + p
+    auto count_ahead = [&](int p, const uint8_t* b, uint32_t cap) -> uint32_t {
+        if (!kStreamed || p + (int)cap <= avail) return warp_common_prefix(src + p, b, cap);
+        uint32_t L = 0;
+        for (;;) {
+            wait_for((long long)p + L + 1);
+            const uint32_t piece = min(cap - L, (uint32_t)(avail - (p + (int)L)));
+            const uint32_t x = warp_common_prefix(src + p + L, b + L, piece);
+            L += x;
+            if (x < piece || L == cap) return L;
+        }
+    };
 
     // ---- position table access (classic: u32 per bucket; compact: see above)
     uint32_t tbase = in.tbase;
@@ -373,6 +415,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
         };
         auto l2_prefetch = [&](int ip) {       // keep the next kPrefetchAhead bytes of input on their way into L2
             if (pf_next < (uint32_t)ip) pf_next = (uint32_t)ip & ~(kPrefetchChunk - 1);
+            if (kStreamed && avail < n && pf_next + kPrefetchChunk > (uint32_t)avail) return;   // not there yet (no poll here: wait_for refreshes avail)
             if (pf_next < (uint32_t)n) {
                 const uintptr_t pbase = (base + pf_next) & ~uintptr_t(15);
                 const uint32_t room = (uint32_t)n - pf_next;
@@ -383,6 +426,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
         };
         auto move_window = [&](int ip) {       // (re)centre the window on ip's line
             const uintptr_t L = (base + (uintptr_t)ip) >> 7;
+            if (kStreamed) wait_for((long long)((L + 3) << 7) - (long long)base);       // lines L-1 .. L+2 are touched below
             __syncwarp();
             cp_async_wait<0>();
             __syncwarp();
@@ -557,13 +601,13 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
                 const uint32_t sb = __ballot_sync(kFull, (nb < 4) || (at + 4 >= cap1));   // never empty
                 const uint32_t res = __shfl_sync(kFull, at + nb, __ffs(sb) - 1);
                 L = res < cap1 ? res : cap1;
-                if (res >= cap1 && cap > 128u) L += warp_common_prefix(src + p + 128, cand + 128, cap - 128u);
+                if (res >= cap1 && cap > 128u) L += count_ahead(p + 128, cand + 128, cap - 128u);
             } else {                                                                                 // candidate in the dictionary
                 cand = in.dict_end - (S - m); room_c = in.dict_len - (S - m);
                 cap = min(cap, (uint32_t)(in.dict_end - cand));
-                L = warp_common_prefix(src + p, cand, cap);
+                L = count_ahead(p, cand, cap);
                 if (L >= 4 && L == cap && (int)(p + L) < mlimit)                                     // :1085-1089
-                    L += warp_common_prefix(src + p + L, src, (uint32_t)(mlimit - (p + (int)L)));
+                    L += count_ahead(p + (int)L, src, (uint32_t)(mlimit - (p + (int)L)));
             }
             if (L < 4) return false;                                                                 // :1009 / :1189
             uint32_t back = 0;
@@ -614,7 +658,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
                 L = 32u;
                 if (cap > 32u) {
                     if (kWide && cpos >= lo_pos) L += count_wide(p + 32, cpos + 32, cap - 32u);
-                    else L += warp_common_prefix(src + p + 32, src + cpos + 32, cap - 32u);
+                    else L += count_ahead(p + 32, src + cpos + 32, cap - 32u);
                 }
             }
             if (L < 4) return false;                                                                 // :1189
@@ -622,6 +666,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
             return true;
         };
 
+        wait_for(128);
         { t_sweep_to(S); uint2 v = ldg_5bytes(src); t_put(hash5(v.x, v.y), S); }    // :924
         __syncwarp();
         int ip = 1;                            // :925  (search runs start here)
@@ -662,6 +707,10 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
                     else if (jbase == 1) { off = off1; step = (int)step1; }
                     else probe_schedule(jbase + lane, in.accel, off, step);
                     const long long pos64 = (long long)ip + off;
+                    if (kStreamed && avail < n) {       // the window's farthest probe reads 8 bytes at its position
+                        const long long far = __shfl_sync(kFull, pos64, (int)width - 1);
+                        wait_for(far + 8);
+                    }
                     const bool active = lane < width;
                     bool valid = active && (pos64 + step <= (long long)mfl);                         // :969
                     bool clipped = false;               // compact table: probes past the epoch boundary wait for the sweep
@@ -742,9 +791,9 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
                 if (maxback) { b_src = __ldg(src + mpos - 1); b_cand = __ldg(cand - 1); }
                 uint32_t cap = (uint32_t)(mlimit - mpos);
                 if (in_dict) cap = min(cap, (uint32_t)(in.dict_end - cand));
-                uint32_t L = 4 + warp_common_prefix(src + mpos + 4, cand + 4, cap - 4);
+                uint32_t L = 4 + count_ahead(mpos + 4, cand + 4, cap - 4);
                 if (in_dict && L == cap && mpos + (int)L < mlimit)
-                    L += warp_common_prefix(src + mpos + L, src, (uint32_t)(mlimit - (mpos + (int)L)));
+                    L += count_ahead(mpos + (int)L, src, (uint32_t)(mlimit - (mpos + (int)L)));
                 const uint32_t back = (b_src == b_cand) ? warp_common_suffix(src + mpos, cand, maxback) : 0u;
                 mip = mpos - (int)back;
                 mlen = L + back; dist = (S + (uint32_t)mpos) - midx;
@@ -769,7 +818,7 @@ __device__ void find_block(BlockIn& in, uint32_t* table, const uint32_t data_s, 
     out.push((uint32_t)anchor, (uint32_t)(n - anchor), 0u, 0u, in.block);
 }
 
-template <bool kWide, bool kCompact>
+template <bool kWide, bool kCompact, bool kStreamed = false>
 __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ring, uint16_t* hring, Queue* q)
 {
     const uint32_t lane = lane_id();
@@ -856,9 +905,15 @@ __device__ void finder_main(const CompressArgs& a, uint32_t* table, uint32_t* ri
                     __syncwarp();
                 }
                 if (dict_len >= 1 && dict_len <= 3) dict_len = 0;                            // :1581-1587
-                BlockIn in{src, n, dict_end, dict_len, offset, accel, b, w_end, w_lo, w_ok, tbase};
+                BlockIn in{src, n, dict_end, dict_len, offset, accel, b, w_end, w_lo, w_ok, tbase, a.arrived, a.seg_bytes, 0, false};
                 if (n > 0) offset += (uint32_t)n;                                            // :918 (n == 0 never reaches it, :1263-1273)
-                find_block<kWide, kCompact>(in, table, data_s, hash_s, out, (uint32_t)off0, (uint32_t)step0, (uint32_t)off1, (uint32_t)step1);
+                const long long t_begin = kStreamed ? clock64() : 0;
+                find_block<kWide, kCompact, kStreamed>(in, table, data_s, hash_s, out, (uint32_t)off0, (uint32_t)step0, (uint32_t)off1, (uint32_t)step1);
+                if (kStreamed && a.busy_cycles && lane == 0) {      // what the host's copy schedule is tuned by: finder time net of waiting
+                    atomicAdd(a.busy_cycles, (unsigned long long)(clock64() - t_begin - in.stall));
+                    atomicAdd(a.busy_cycles + 1, (unsigned long long)n);
+                    if (in.timed_out) atomicAdd(a.busy_cycles + 2, 1ull);
+                }
                 w_end = in.w_end; w_lo = in.w_lo; w_ok = in.w_ok; tbase = in.tbase;
                 __syncwarp();
                 dict_end = src + n; dict_len = (uint32_t)n;                                  // :1633-1634
@@ -1010,6 +1065,33 @@ compress_kernel(CompressArgs a)
     }
 }
 
+// Streamed launches (host batch calls, see api.cu): the classic geometry, finders wait for their input segment by segment.
+__global__ void __launch_bounds__(kPairs * 64, 3)
+compress_kernel_streamed(CompressArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_dyn[];
+    uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint16_t* hrings = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw + kPairs * kHashPos * sizeof(uint16_t));
+    uint32_t* tables = rings + kPairs * kWinWords;
+    Queue* queues = reinterpret_cast<Queue*>(tables + kPairs * kHashEntries);
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t pair = warp & (kPairs - 1);
+    if (threadIdx.x < kPairs) {
+        Queue* q = &queues[threadIdx.x];
+        mbar_init(&q->full[0], 1); mbar_init(&q->full[1], 1);
+        mbar_init(&q->empty[0], 1); mbar_init(&q->empty[1], 1);
+    }
+    __syncthreads();
+    if (warp < kPairs) finder_main<false, false, true>(a, tables + pair * kHashEntries, rings + pair * kWinWords, hrings + pair * kHashPos, &queues[pair]);
+    else emitter_main(a, &queues[pair]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t done = atomicAdd(&a.scratch->work_counter[1], 1u);
+        if (done == gridDim.x - 1) { a.scratch->work_counter[0] = 0; a.scratch->work_counter[1] = 0; __threadfence(); }
+    }
+}
+
 // Compact mode: the dense kernel with 8.5 KiB position tables (see find_block): 4 CTAs of 4 pairs per SM = 16 streams in
 // flight per SM instead of 12.  Used for launches of more than one wave of the classic kernel.
 constexpr int kCompactTableBytes = kHashEntries * 2 + kHashEntries / 8;      // u16 entries + epoch bits
@@ -1070,7 +1152,47 @@ compress_kernel_wide(CompressArgs a)
     }
 }
 
+__global__ void set_flag_kernel(uint32_t* flag, uint32_t v) { *flag = v; __threadfence(); }
+
+// Stream-aliasing self-test (api.cu: probe_stream_aliasing): spins until *flag != 0 or `timeout` cycles have passed and
+// reports which; `successor_kernel` is the entry queued behind it in the same stream.
+__global__ void alias_probe_kernel(const uint32_t* flag, uint32_t* result, long long timeout)
+{
+    const long long t0 = clock64();
+    uint32_t v = 0;
+    for (;;) {
+        v = ld_acquire_sys(flag);
+        if (v || clock64() - t0 > timeout) break;
+        __nanosleep(500);
+    }
+    *result = v ? 1u : 2u;
+}
+__global__ void successor_kernel(uint32_t* result) { result[1] = 1u; }
+
 }  // namespace
+
+// stream-ordered store of one arrival flag (the alternative to a 4-byte copy: B200LZ4_STREAM_FLAG=kernel)
+cudaError_t launch_set_flag(uint32_t* flag, uint32_t v, cudaStream_t stream)
+{
+    set_flag_kernel<<<1, 1, 0, stream>>>(flag, v);
+    return cudaGetLastError();
+}
+
+cudaError_t preload_compress_kernels()
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, compress_kernel_streamed);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, set_flag_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, compress_kernel);
+    return e;
+}
+
+cudaError_t launch_alias_probe(const uint32_t* flag, uint32_t* result, long long timeout_cycles, cudaStream_t stream)
+{
+    alias_probe_kernel<<<1, 1, 0, stream>>>(flag, result, timeout_cycles);
+    successor_kernel<<<1, 1, 0, stream>>>(result);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
 {
@@ -1086,6 +1208,8 @@ cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
         if (!configured[dev]) {
             e = cudaFuncSetAttribute(compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(compress_kernel_streamed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(compress_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(compress_kernel_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCompactSmem);
@@ -1099,6 +1223,11 @@ cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream)
         }
     }
     if (a.n_streams <= 0) return cudaSuccess;
+    if (a.arrived) {                             // input still arriving: classic geometry, finders poll a.arrived
+        const int want = (a.n_streams + kPairs - 1) / kPairs, max_ctas = sm_count * 3;
+        compress_kernel_streamed<<<want < max_ctas ? want : max_ctas, kPairs * 64, smem, stream>>>(a);
+        return cudaGetLastError();
+    }
     static const bool no_wide = getenv("B200LZ4_NO_WIDE") != nullptr;     // A/B switch for measurements
     if (a.n_streams <= sm_count && !no_wide) {   // few streams: one per SM with everything in shared memory
         compress_kernel_wide<<<a.n_streams, 64, kWideSmem, stream>>>(a);

@@ -237,9 +237,32 @@ struct Copier {
     }
 };
 
+// kPublish (streamed host call, api.cu: decompress_host_streamed): the launch's blocks all have the same capacity and the
+// host sends their output home segment by segment while they are still being decoded.  Whenever a block's flushed
+// prefix crosses a segment boundary the copier counts it in seg_count[s]; the block that completes segment s for the
+// whole launch raises host_ready[s] (page-locked host memory the calling thread polls).
+template <bool kPublish>
 __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, uint32_t out_s)
 {
     const uint32_t lane = lane_id();
+    int pub = 0;                            // segments of the current block already counted
+    auto publish = [&](int upto) {          // upto: number of leading segments of the current block that are in global memory
+        if (!kPublish) return;
+        if (pub >= upto) return;
+        __threadfence();                    // every lane's stores of those segments are visible device-wide ...
+        __syncwarp();
+        if (lane == 0) {
+            for (int sgm = pub; sgm < upto; sgm++) {
+                const uint32_t before = atomicAdd(a.seg_count + sgm, 1u);       // ... before the block is counted
+                if (before + 1u == (uint32_t)a.n_streams) {
+                    __threadfence_system();
+                    *(volatile uint32_t*)(a.host_ready + sgm) = 1u;
+                }
+            }
+        }
+        __syncwarp();
+        pub = upto;
+    };
     Copier C;
     C.in_s = in_s; C.out_s = out_s; C.dst = nullptr; C.oskew = 0; C.op = 0; C.flushed = 0; C.ring_lo = 0;
     C.dict_end = nullptr; C.dict_len = 0; C.cap = 0;
@@ -259,6 +282,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
             const BlockGeom g = block_geom(a, blk);
             C.dst = g.out; C.oskew = (uint32_t)(reinterpret_cast<uintptr_t>(g.out) & 15); C.cap = g.cap;
             C.op = 0; C.flushed = 0; C.ring_lo = 0;
+            pub = 0;
             gbase = g.payload - (reinterpret_cast<uintptr_t>(g.payload) & 15);
             if (cf & kStreamBegin) {
                 const DState* st = a.states ? reinterpret_cast<const DState*>(a.states[q->stream[b]]) : nullptr;
@@ -323,6 +347,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
             C.op = op; C.flushed = op;
             C.preload(op);
             __syncwarp();
+            if (kPublish && C.flushed >= (pub + 1) * a.seg_bytes) publish(min(C.flushed / a.seg_bytes, a.n_segs - 1));
         } else if (cnt) {
             // ---- up to 32 short sequences
             constexpr uint32_t M = kOutRing - 1;
@@ -333,6 +358,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
             const int m_dst = lit_dst + (int)lit;
             const int from = m_dst - (int)dist;
             C.flush(op0, false);                       // previous batches leave for global memory (128-bit stores)
+            if (kPublish && C.flushed >= (pub + 1) * a.seg_bytes) publish(min(C.flushed / a.seg_bytes, a.n_segs - 1));
             BCHK(a, op0 >= 0 && op1 >= op0 && op1 <= C.cap);
             const int ring_base = max(C.ring_lo, op1 - kOutRing);       // output positions >= this are in the ring; below: in global memory
             const uint32_t oskew = C.oskew;
@@ -417,6 +443,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
 
         if (cf & kEndBlock) {
             if (result >= 0 && dst) { C.flush(C.op, true); __syncwarp(); }
+            if (kPublish) publish(a.n_segs);           // the block is over (short, failed or complete): nothing more will come
             if (lane == 0) a.out_len[blk] = result;
             if (result > 0) { C.dict_end = dst + result; C.dict_len = (uint32_t)result; last_out = dst; last_len = result; }   // cbits/lz4.c:2353-2355
             if ((cf & kStreamEnd) && a.states && last_out) {   // keep the reachable tail of the last output for the next call
@@ -436,7 +463,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
 // Two register budgets: 16 CTAs per SM (64 registers, a few spilled bytes) when a launch has more than 12 streams per SM
 // to keep busy, 12 CTAs per SM (80 registers, no spills) when everything is resident anyway -- measured +6 % on config 2's
 // single wave, -12 % on 16 384 blocks of 64 KiB if used there.
-template <int kCtasPerSm>
+template <int kCtasPerSm, bool kPublish = false>
 __global__ void __launch_bounds__(64, kCtasPerSm)
 decompress_kernel(DecompressArgs a)
 {
@@ -452,7 +479,7 @@ decompress_kernel(DecompressArgs a)
     asm volatile("mov.u32 %0, %1;" : "=r"(in_s) : "r"(smem_u32(in_ring)));
     asm volatile("mov.u32 %0, %1;" : "=r"(out_s) : "r"(smem_u32(out_ring)));
     if (threadIdx.x < 32) parser_main(a, &queue, in_s);
-    else copier_main(a, &queue, in_s, out_s);
+    else copier_main<kPublish>(a, &queue, in_s, out_s);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t done = atomicAdd(&a.scratch->work_counter[3], 1u);
@@ -488,6 +515,14 @@ cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream)
     // them that the narrow kernel would leave most of the GPU idle (measured: 128 streams 17 -> 35 GB/s on mixed data, 11 ->
     // 49 GB/s on text; with more than two streams per SM the narrow kernel's 16 CTAs per SM win).  Independent blocks gain
     // nothing from it -- a block has ONE token chain, so only one of the eight parsers would work.
+    if (a.seg_count) {                      // streamed host call: independent blocks, output leaves segment by segment
+        if (a.n_streams <= sm_count * 12) decompress_kernel<12, true><<<a.n_streams, 64, 0, stream>>>(b);
+        else {
+            const int max_ctas = sm_count * 16;
+            decompress_kernel<16, true><<<a.n_streams < max_ctas ? a.n_streams : max_ctas, 64, 0, stream>>>(b);
+        }
+        return cudaGetLastError();
+    }
     bool wide = a.stream_first != nullptr && a.n_streams <= 2 * sm_count;
     if (wide_env) wide = wide_env[0] == '1';
     if (wide && a.wide_arena) return launch_decompress_wide(b, sm_count, stream);

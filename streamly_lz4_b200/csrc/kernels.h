@@ -13,6 +13,10 @@ struct CompressArgs {
     uint8_t* dst; const int64_t* dst_off; const int32_t* dst_cap; int32_t* out_len;
     int accel; int header;
     Scratch* scratch;
+    // streamed launch (NULL: all input is resident): the launch's blocks are still arriving over PCIe, segment by
+    // segment; *arrived segments of seg_bytes (a multiple of 128) bytes of EVERY block of the launch have landed.
+    // Block starts must be 128-byte aligned.  busy_cycles[0] += finder cycles net of waiting, [1] += bytes.
+    const uint32_t* arrived; int seg_bytes; unsigned long long* busy_cycles;
 };
 
 struct DecompressArgs {
@@ -25,6 +29,9 @@ struct DecompressArgs {
     int debug;                  // measurement switches (B200LZ4_DECODE_DEBUG): 1 = copier skips every copy (parser-bound rate)
     uint4* wide_arena;          // descriptor rings of the wide kernel: wide_ctas x kWideArenaPerCta bytes (NULL: narrow kernel only)
     int wide_ctas;
+    // streamed launch (NULL: off): every block of the launch has the same capacity, cut into n_segs segments of seg_bytes;
+    // seg_count[s] counts the blocks whose segment s is in global memory, the last one sets host_ready[s] (mapped host memory)
+    uint32_t* seg_count; uint32_t* host_ready; int seg_bytes; int n_segs;
 };
 
 // decompress_kernel_wide keeps its parsed-ahead sequence descriptors in global memory (L2): per CTA, kWideParsers rings of
@@ -45,6 +52,10 @@ struct CompactArgs {
 };
 
 cudaError_t launch_compress(const CompressArgs& a, cudaStream_t stream);
+cudaError_t launch_set_flag(uint32_t* flag, uint32_t v, cudaStream_t stream);
+cudaError_t preload_compress_kernels();
+cudaError_t preload_compact_kernels();
+cudaError_t launch_alias_probe(const uint32_t* flag, uint32_t* result, long long timeout_cycles, cudaStream_t stream);
 cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream);
 cudaError_t launch_decompress_wide(const DecompressArgs& a, int sm_count, cudaStream_t stream);
 cudaError_t device_sm_count(int* out);
