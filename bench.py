@@ -438,6 +438,17 @@ def run_gpu(args):
     e2e_wall = time.perf_counter() - t_all0
     e2e_launches = ctx.launch_count() - launches0          # counted by the library: chunks x (codec + scan + gather)
     assert rc == 0 and int(doff[-1]) == comp_total
+    # the same call through the plain chunk pipeline (whole blocks land before their kernel starts), for comparison
+    os.environ["B200LZ4_NO_STREAMED"] = "1"
+    ctx.compress_batch(src_view, offs, lens, ACCEL, HEADER, pin_dst)
+    barrier()
+    t_p0 = time.perf_counter()
+    for _ in range(min(args.steps, 4)):
+        rc, doff, olen = ctx.compress_batch(src_view, offs, lens, ACCEL, HEADER, pin_dst)
+    barrier()
+    e2e_plain_wall = (time.perf_counter() - t_p0) / min(args.steps, 4)
+    del os.environ["B200LZ4_NO_STREAMED"]
+    assert rc == 0 and int(doff[-1]) == comp_total
     clocks = sampler.stop() if rank == 0 else None
     ceiling = copy_ceiling(ctx, pin_src, total, ctx.pinned("b_probe", comp_total), comp_total, 5, barrier)
 
@@ -552,6 +563,7 @@ def run_gpu(args):
 
     total_ms = rmax(total_ms)
     e2e_wall = rmax(e2e_wall)
+    e2e_plain_max = rmax(e2e_plain_wall)
     ms_per_step = total_ms / args.steps
     value = world * total / (ms_per_step / 1e3) / 1e9
     e2e_value = world * total / (e2e_wall / args.steps) / 1e9
@@ -610,17 +622,20 @@ def run_gpu(args):
                        "parallelism": f"block stripes over {world} GPU(s), no collective", "host_numa": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total + 20 * n,
                     "d2h_bytes_per_step": comp_total + 12 * n + 8,
-                    "api": "b200lz4_compress_batch (pinned host in/out)",
+                    "api": "b200lz4_compress_batch (pinned host in/out; streamed call: blocks reach the device segment by segment in "
+                           "deadline order while their finders run, see DESIGN.md section 5)",
                     "h2d_ms": statistics.mean(split["h2d_ms"]), "kernel_ms": statistics.mean(split["kernel_ms"]),
                     "d2h_ms": statistics.mean(split["d2h_ms"]), "wall_ms_per_step": 1e3 * e2e_wall / args.steps,
                     "copy_ceiling": {"value": ceiling_gbps, "unit": UNIT, "ms": ceil_ms, "h2d_alone_ms": h2d_ms_alone,
                                      "what": "plain cudaMemcpyAsync of the same H2D and D2H bytes on two streams, all ranks at once, "
                                              "max over ranks"},
-                    "frac_of_copy_ceiling": e2e_value / ceiling_gbps},
+                    "frac_of_copy_ceiling": e2e_value / ceiling_gbps,
+                    "plain_pipeline": {"value": world * total / e2e_plain_max / 1e9, "unit": UNIT, "wall_ms_per_step": 1e3 * e2e_plain_max,
+                                       "what": "same call with B200LZ4_NO_STREAMED=1: six chunks, each kernel starts when its whole chunk has landed"}},
             "e2e_staged": None if staged is None else dict(staged, value=world * total / (staged["wall_ms_per_step"] / 1e3) / 1e9, unit=UNIT),
             "gpu_launches": gpu_launches + e2e_launches + gpu_launches_extra + (staged["launches"] * max(2, min(args.steps, 5)) if staged else 0),
             "gpu_launches_detail": {"timed_value_region": gpu_launches, "e2e_region": e2e_launches,
-                                    "per_step": "compress_kernel + scan_kernel + gather_kernel (e2e: per pipeline chunk)"},
+                                    "per_step": "compress_kernel + scan_kernel + gather_kernel (e2e: per block group, plus one flag kernel per copied piece)"},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
             "extra": {k: v for k, v in extra.items() if v is not None},
         }

@@ -93,6 +93,9 @@ struct b200lz4_ctx {
     double est_h2d_gbs = 0;                 // H2D bandwidth of the last streamed call
     int clock_khz = 0;
     int streamed_calls = 0;
+    cudaStream_t fstream = nullptr;         // arrival flags are raised from here (set_flag kernels behind per-piece events), so that
+                                            // the copy stream's pieces run back to back
+    std::vector<cudaEvent_t> ev_piece;
     int n_kgood = -1;                       // kernel streams verified not to share a hardware queue with the copy streams
                                             // or with each other (-1: not probed yet); they come first in kstream[]
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
@@ -164,6 +167,7 @@ int sync_all(b200lz4_ctx* c)
     CU(cudaStreamSynchronize(c->stream));
     for (auto& k : c->kstream) CU(cudaStreamSynchronize(k));
     CU(cudaStreamSynchronize(c->dstream));
+    if (c->fstream) CU(cudaStreamSynchronize(c->fstream));
     return 0;
 }
 
@@ -175,13 +179,17 @@ int sync_all(b200lz4_ctx* c)
 // kernel is bound by per-block latency, not by the number of blocks it is given.
 struct Chunk { int b0, b1, s0, s1; int64_t lo, hi; };
 
-int plan_chunks(const int64_t* off, const int32_t* len, int n, const int32_t* first, int ns, Chunk* out)
+int plan_chunks(const int64_t* off, const int32_t* len, int n, const int32_t* first, int ns, Chunk* out, bool early_start = false)
 {
     int64_t total = 0;
     for (int i = 0; i < n; i++) total += len[i];
     // Chunk k becomes ready when its H2D copy lands and finishes one block latency later, so the end of the
     // call is "last byte arrives + block latency + D2H of the last chunk": keep the last chunk small.
-    static const double kShare[kMaxChunks] = {0.14, 0.20, 0.20, 0.20, 0.18, 0.08};
+    // early_start (mirrored decompress: the output leaves from inside the kernels, so the call ends one PCIe-bound stretch
+    // after the FIRST chunk has landed): a small first chunk instead of a small last one
+    static const double kShareTail[kMaxChunks] = {0.14, 0.20, 0.20, 0.20, 0.18, 0.08};
+    static const double kShareHead[kMaxChunks] = {0.03, 0.09, 0.18, 0.24, 0.24, 0.22};
+    const double* kShare = early_start ? kShareHead : kShareTail;
     const bool small = total < (int64_t(48) << 20);
     int k = 0, unit = 0;
     const int units = first ? ns : n;
@@ -261,6 +269,14 @@ int probe_stream_aliasing(b200lz4_ctx* c)
         (bad ? rejected : good).push_back(cand);
     }
     while (next_existing < kKernelStreams) rejected.push_back(c->kstream[next_existing++]);
+    // the flag stream must not sit behind a waiting kernel either
+    for (int t = 0; t < 16 && !c->fstream; t++) {
+        cudaStream_t cand;
+        CU(cudaStreamCreateWithFlags(&cand, cudaStreamNonBlocking));
+        bool bad = false;
+        for (size_t j = 0; j < good.size() && !bad; j++) if ((rc = streams_alias(c, good[j], cand, true, &bad))) return rc;
+        if (bad) cudaStreamDestroy(cand); else c->fstream = cand;
+    }
     c->n_kgood = (int)good.size();
     int k = 0;
     for (cudaStream_t x : good) c->kstream[k++] = x;
@@ -269,29 +285,16 @@ int probe_stream_aliasing(b200lz4_ctx* c)
     return 0;
 }
 
-// One segment of every block of a group: `rows` ranges of `width` bytes at constant pitches.  Either one pitched copy
-// (cudaMemcpy2DAsync) or one batch of plain 1-D copies (cudaMemcpyBatchAsync, CUDA 12.8+): the copy engine moves a pitched
-// copy row by row, which measured 15 % slower than plain copies while the opposite direction is busy.
-int copy_rows(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t spitch, size_t width, size_t rows, cudaMemcpyKind kind,
-              cudaStream_t st, bool batch)
+// One segment of every block of a group: `rows` ranges of `width` bytes at constant pitches, as one pitched copy.  (The copy
+// engine moves a pitched copy row by row: measured 9 % slower than one plain copy of the same bytes on an idle link and
+// 15 % slower while the opposite direction is busy, which is why segments are not made smaller than they have to be.)
+int copy_rows(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t spitch, size_t width, size_t rows, cudaMemcpyKind kind, cudaStream_t st)
 {
     if (rows == 0 || width == 0) return 0;
-    if (!batch || rows == 1) {
-        if (rows == 1) CU(cudaMemcpyAsync(dst, src, width, kind, st));
-        else CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st));
-        return 0;
-    }
-    thread_local std::vector<void*> d, s2;
-    thread_local std::vector<size_t> sz;
-    d.resize(rows); s2.resize(rows); sz.assign(rows, width);
-    for (size_t r = 0; r < rows; r++) { d[r] = dst + r * dpitch; s2[r] = const_cast<uint8_t*>(src) + r * spitch; }
-    cudaMemcpyAttributes at{};
-    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-    size_t idx = 0, fail_idx = 0;
-    CU(cudaMemcpyBatchAsync(d.data(), s2.data(), sz.data(), rows, &at, &idx, 1, &fail_idx, st));
+    if (rows == 1 || (width == dpitch && width == spitch)) CU(cudaMemcpyAsync(dst, src, width * rows, kind, st));
+    else CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st));
     return 0;
 }
-inline bool stream_copy_batch() { const char* e = getenv("B200LZ4_STREAM_COPY"); return e ? e[0] == 'b' : false; }
 
 // ---- streamed compress call ---------------------------------------------------
 // A batch of equally long independent blocks at a constant pitch (what compressChunks over fixed-size reads produces)
@@ -313,7 +316,7 @@ constexpr int kStreamedGaveUp = -1000;  // internal: compress_host retries throu
 StreamShape streamed_shape(const int64_t* off, const int32_t* len, int n, const int32_t* stream_first, const int32_t* block_cap)
 {
     StreamShape r{0, 0, false};
-    static const bool off_env = getenv("B200LZ4_NO_STREAMED") != nullptr;
+    const bool off_env = getenv("B200LZ4_NO_STREAMED") != nullptr;      // (read per call: bench.py times both pipelines in one process)
     if (off_env || stream_first || block_cap || n < 96) return r;
     const int L = len[0];
     if (L < 65536 || (int64_t)L * n < (int64_t(96) << 20)) return r;
@@ -344,7 +347,8 @@ int compress_host_streamed(b200lz4_ctx* c, const void* src, const int64_t* src_o
     const char* env_s = getenv("B200LZ4_STREAM_S");
     const char* env_f = getenv("B200LZ4_STREAM_FLAG");
     const bool flag_by_kernel = env_f && env_f[0] == 'k';
-    const bool batch_copies = stream_copy_batch();
+    const bool flag_inline_copy = env_f && env_f[0] == 'c';
+    const bool flag_separate = !flag_by_kernel && !flag_inline_copy && c->fstream != nullptr;
     const double ns_per_byte = c->est_ns_per_byte > 0 ? c->est_ns_per_byte : 12.0;       // first call: ~85 MB/s per finder
     const double h2d_gbs = c->est_h2d_gbs > 0 ? c->est_h2d_gbs : 50.0;
     const double t_block_ms = ns_per_byte * 1.1 * L * 1e-6, t_h2d_ms = (double)total / (h2d_gbs * 1e6);
@@ -352,7 +356,9 @@ int compress_host_streamed(b200lz4_ctx* c, const void* src, const int64_t* src_o
     int G = env_g ? atoi(env_g) : (rho <= 0.45 ? 2 * nks : nks);        // a group runs behind group g - nks on its stream
     if (G < 1) G = 1;
     if (G > kMaxGroups) G = kMaxGroups;
-    int S = env_s ? atoi(env_s) : 8;
+    // segments of ~160 000 bytes (rows of a pitched copy: smaller ones cost copy-engine efficiency while the D2H direction is
+    // busy, larger ones lengthen the tail, which is one segment's worth of finder time): 4 for 640 000-byte blocks, 16 from 2.5 MB
+    int S = env_s ? atoi(env_s) : (int)std::min<int64_t>(kMaxSegs, std::max<int64_t>(4, ((int64_t)L + 80000) / 160000));
     if (S < 1) S = 1;
     if (S > kMaxSegs) S = kMaxSegs;
     const int seg = (int)((((int64_t)L + S - 1) / S + 127) / 128 * 128);
@@ -421,8 +427,16 @@ int compress_host_streamed(b200lz4_ctx* c, const void* src, const int64_t* src_o
             if (wl > 0) CU(cudaMemcpyAsync(d_src + DP * (n - 1) + lo, hsrc + src_off[n - 1] + lo, (size_t)wl, cudaMemcpyHostToDevice, st));
         }
         if (rows > 0 && (rc = copy_rows(d_src + DP * b0 + lo, (size_t)DP, hsrc + src_off[b0] + lo, (size_t)shp.P, (size_t)width, (size_t)rows,
-                                        cudaMemcpyHostToDevice, st, batch_copies))) return rc;
-        if (flag_by_kernel) CU(launch_set_flag(c->d_flags + pc.g, (uint32_t)(pc.s + 1), st));
+                                        cudaMemcpyHostToDevice, st))) return rc;
+        if (flag_separate) {                // the flag is raised from another stream: the next piece starts right behind this one
+            const size_t pi = (size_t)(&pc - pieces.data());
+            while (c->ev_piece.size() <= pi) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_piece.push_back(e); }
+            CU(cudaEventRecord(c->ev_piece[pi], st));
+            CU(cudaStreamWaitEvent(c->fstream, c->ev_piece[pi], 0));
+            CU(launch_set_flag(c->d_flags + pc.g, (uint32_t)(pc.s + 1), c->fstream));
+            c->launches++;
+        }
+        else if (flag_by_kernel) CU(launch_set_flag(c->d_flags + pc.g, (uint32_t)(pc.s + 1), st));
         else CU(cudaMemcpyAsync(c->d_flags + pc.g, c->h_const + (pc.s + 1), sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         if (pc.s != 0) continue;
         // first segment of the group is on its way: queue the group's kernels behind it
@@ -700,9 +714,24 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     if (streams) for (int s = 0; s < n_streams; s++)
         if (!streams[s] || streams[s]->ctx != c) return fail(B200LZ4_E_ARG, "stream handle belongs to another ctx");
     const uint8_t* hsrc = static_cast<const uint8_t*>(src);
+    // How the output goes home (B200LZ4_DECODE_OUT): "copy" = D2H copies behind each chunk's kernel; "pieces" = segment by
+    // segment while the blocks are being decoded (decompress_host_streamed; equally large independent blocks; the default
+    // where it applies); "mirror" = independent blocks with their sizes in the headers, page-locked destination: the copier
+    // warps store every output byte to the host buffer as well as to HBM (decompress.cu: kMirror) and no D2H copy follows.
+    // Measured on config 2 (1.07 GB out, 0.77 GB in): copy 27.7 ms, mirror 27.0 ms (the posted writes of 1 678 CTAs reach
+    // 40 GB/s and slow the H2D copy from 15 to 18.5 ms), pieces 26.4 ms -- so mirror stays opt-in.
+    const bool no_streamed = getenv("B200LZ4_NO_STREAMED") != nullptr;
+    const char* out_env = getenv("B200LZ4_DECODE_OUT");
+    uint8_t* mirror_dst = nullptr;
+    const char* dwide_env = getenv("B200LZ4_DWIDE");            // (tests force the wide kernel with it: that one has no mirror)
+    if (out_env && out_env[0] == 'm' && header == 8 && !stream_first && !streams && !(dwide_env && dwide_env[0] == '1')) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, dst) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+            mirror_dst = static_cast<uint8_t*>(pa.devicePointer);
+        else cudaGetLastError();
+    }
     // equally large independent blocks with their size in the header: the output leaves segment by segment
-    static const bool no_streamed = getenv("B200LZ4_NO_STREAMED") != nullptr;
-    if (!no_streamed && header == 8 && !stream_first && !streams && n >= 96 && src_len[0] >= 8) {
+    if (!mirror_dst && !no_streamed && !(out_env && out_env[0] == 'c') && header == 8 && !stream_first && !streams && n >= 96 && src_len[0] >= 8) {
         const int L = le32(hsrc + src_off[0] + 4);
         bool ok = L >= 65536 && (int64_t)L * n >= (int64_t(96) << 20);
         int cap_last = 0;
@@ -713,7 +742,7 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
         if (ok) return decompress_host_streamed(c, src, src_off, src_len, n, L, cap_last, dst, dst_cap, dst_off, out_len);
     }
     Chunk chunks[kMaxChunks];
-    const int nchunks = plan_chunks(src_off, src_len, n, stream_first, ns, chunks);
+    const int nchunks = plan_chunks(src_off, src_len, n, stream_first, ns, chunks, mirror_dst != nullptr);
 
     Carver cv;
     const size_t o_src_off = cv.take(sizeof(int64_t) * n);
@@ -750,7 +779,7 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     if (streams) { void** hs = reinterpret_cast<void**>(hd + o_states); for (int s = 0; s < ns; s++) hs[s] = streams[s]->d_state; }
 
     if ((rc = c->d_src.ensure((size_t)src_bytes + 64))) return rc;
-    if ((rc = c->d_slots.ensure((size_t)slots_total + 64))) return rc;
+    if ((rc = c->d_slots.ensure((size_t)slots_total + 64 + 16))) return rc;
     if (!contiguous && (rc = c->d_out.ensure((size_t)slots_total + 64))) return rc;
     // descriptor rings for chunks the wide kernel may take (few streams): one slice of one CTA-arena per stream, per chunk
     int wide_first[kMaxChunks + 1] = {0};
@@ -761,6 +790,7 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
     if ((rc = c->d_wide.ensure((size_t)wide_first[nchunks] * kWideArenaPerCta))) return rc;
     uint8_t* d_src = static_cast<uint8_t*>(c->d_src.p);
     uint8_t* d_slots = static_cast<uint8_t*>(c->d_slots.p);
+    if (mirror_dst) d_slots += reinterpret_cast<uintptr_t>(mirror_dst) & 15;      // same address modulo 16 on both sides: 128-bit stores line up
     uint8_t* d_out = static_cast<uint8_t*>(c->d_out.p);
     int64_t* d_out_off = reinterpret_cast<int64_t*>(dd + o_out_off);
     int32_t* d_out_len = reinterpret_cast<int32_t*>(dd + o_out_len);
@@ -792,6 +822,7 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
         a.header = header; a.max_block = max_block; a.scratch = c->scratch + k;
         a.wide_arena = reinterpret_cast<uint4*>(static_cast<uint8_t*>(c->d_wide.p) + (size_t)wide_first[k] * kWideArenaPerCta);
         a.wide_ctas = wide_first[k + 1] - wide_first[k];
+        a.host_dst = mirror_dst;
         CU(launch_decompress(a, ks));
         c->launches += kernel_launches_per_decompress();
         const int nk = ch.b1 - ch.b0;
@@ -806,7 +837,7 @@ int decompress_host(b200lz4_ctx* c, const void* src, int64_t src_bytes,
                            sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, ks));
         if (k == nchunks - 1) CU(cudaEventRecord(c->ev[2], ks));
         CU(cudaEventRecord(c->ev_k[k], ks));
-        if (contiguous) {   // sizes are known from the headers: the D2H copy can be queued right away
+        if (contiguous && !mirror_dst) {   // sizes are known from the headers: the D2H copy can be queued right away
             const int64_t lo = h_slot_off[ch.b0];
             const int64_t hi = (ch.b1 < n) ? h_slot_off[ch.b1] : slots_total;
             CU(cudaStreamWaitEvent(c->dstream, c->ev_k[k], 0));
@@ -948,7 +979,6 @@ int decompress_host_streamed(b200lz4_ctx* c, const void* src, const int64_t* src
     int remaining = G * S;
     uint8_t* hdst = static_cast<uint8_t*>(dst);
     const bool dbg = getenv("B200LZ4_DEBUG") != nullptr;
-    const bool batch_copies = stream_copy_batch();
     struct PieceLog { int g, s; double issued_ms; cudaEvent_t done; };
     std::vector<PieceLog> plog;
     const auto t_host0 = std::chrono::steady_clock::now();
@@ -962,7 +992,7 @@ int decompress_host_streamed(b200lz4_ctx* c, const void* src, const int64_t* src
             if (wl > 0) CU(cudaMemcpyAsync(hdst + (int64_t)L * (n - 1) + lo, d_slots + (int64_t)L * (n - 1) + lo, (size_t)wl, cudaMemcpyDeviceToHost, c->dstream));
         }
         if (rows > 0) return copy_rows(hdst + (int64_t)L * b0 + lo, (size_t)L, d_slots + (int64_t)L * b0 + lo, (size_t)L, (size_t)width, (size_t)rows,
-                                       cudaMemcpyDeviceToHost, c->dstream, batch_copies);
+                                       cudaMemcpyDeviceToHost, c->dstream);
         return 0;
     };
     long spins = 0;
@@ -1098,6 +1128,8 @@ void b200lz4_ctx_destroy(b200lz4_ctx* c)
     if (c->ev_d0) cudaEventDestroy(c->ev_d0);
     if (c->ev_d1) cudaEventDestroy(c->ev_d1);
     for (auto& k : c->kstream) if (k) cudaStreamDestroy(k);
+    if (c->fstream) cudaStreamDestroy(c->fstream);
+    for (auto& e : c->ev_piece) if (e) cudaEventDestroy(e);
     if (c->dstream) cudaStreamDestroy(c->dstream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

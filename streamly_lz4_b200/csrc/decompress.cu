@@ -187,6 +187,7 @@ __device__ void parser_main(const DecompressArgs& a, DQueue* q, uint32_t ring_s)
 struct Copier {
     uint32_t in_s, out_s;       // shared addresses of the rings
     uint8_t* dst;               // output of the current block
+    uint8_t* hdst;              // kMirror: the block's place in the caller's page-locked HOST buffer (same address modulo 16 as dst)
     uint32_t oskew;             // (address of dst) & 15: ring index of output position q is (q + oskew) & (kOutRing - 1)
     int op;                     // output bytes produced so far
     int flushed;                // output positions below this are in global memory
@@ -211,7 +212,10 @@ struct Copier {
         }
         ring_lo = upto - 64;
     }
-    // ring -> global for output positions [flushed, upto); unless `all`, stops at the last 16-byte boundary
+    // ring -> global for output positions [flushed, upto); unless `all`, stops at the last 16-byte boundary.
+    // kMirror: every store goes to the host buffer as well (posted PCIe writes, 512 contiguous bytes per warp instruction), so
+    // the output is on its way home while the block is still being decoded and no D2H copy follows the kernel.
+    template <bool kMirror>
     __device__ void flush(int upto, bool all)
     {
         const uint32_t lane = lane_id();
@@ -223,16 +227,18 @@ struct Copier {
 #endif
         uint32_t head = (16u - (((uint32_t)lo + oskew) & 15u)) & 15u;
         if (head > (uint32_t)(hi - lo)) head = (uint32_t)(hi - lo);
-        if (lane < head) dst[lo + (int)lane] = (uint8_t)lds8(oidx(lo + (int)lane));
+        if (lane < head) { const uint8_t bb = (uint8_t)lds8(oidx(lo + (int)lane)); dst[lo + (int)lane] = bb; if (kMirror) hdst[lo + (int)lane] = bb; }
         lo += (int)head;
         const uint32_t nvec = (uint32_t)(hi - lo) >> 4;
         for (uint32_t v = lane; v < nvec; v += 32) {
             const int qv = lo + (int)(v << 4);
-            *reinterpret_cast<uint4*>(dst + qv) = lds128(oidx(qv));
+            const uint4 x = lds128(oidx(qv));
+            *reinterpret_cast<uint4*>(dst + qv) = x;
+            if (kMirror) *reinterpret_cast<uint4*>(hdst + qv) = x;
         }
         lo += (int)(nvec << 4);
         const uint32_t tail = (uint32_t)(hi - lo);
-        if (lane < tail) dst[lo + (int)lane] = (uint8_t)lds8(oidx(lo + (int)lane));
+        if (lane < tail) { const uint8_t bb = (uint8_t)lds8(oidx(lo + (int)lane)); dst[lo + (int)lane] = bb; if (kMirror) hdst[lo + (int)lane] = bb; }
         flushed = hi;
     }
 };
@@ -241,7 +247,7 @@ struct Copier {
 // host sends their output home segment by segment while they are still being decoded.  Whenever a block's flushed
 // prefix crosses a segment boundary the copier counts it in seg_count[s]; the block that completes segment s for the
 // whole launch raises host_ready[s] (page-locked host memory the calling thread polls).
-template <bool kPublish>
+template <bool kPublish, bool kMirror>
 __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, uint32_t out_s)
 {
     const uint32_t lane = lane_id();
@@ -264,7 +270,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
         pub = upto;
     };
     Copier C;
-    C.in_s = in_s; C.out_s = out_s; C.dst = nullptr; C.oskew = 0; C.op = 0; C.flushed = 0; C.ring_lo = 0;
+    C.in_s = in_s; C.out_s = out_s; C.dst = nullptr; C.hdst = nullptr; C.oskew = 0; C.op = 0; C.flushed = 0; C.ring_lo = 0;
     C.dict_end = nullptr; C.dict_len = 0; C.cap = 0;
     const uint8_t* gbase = nullptr;         // global address of input ring-space position 0
     const uint8_t* last_out = nullptr; int last_len = 0;
@@ -281,6 +287,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
         if (cf & kBegin) {
             const BlockGeom g = block_geom(a, blk);
             C.dst = g.out; C.oskew = (uint32_t)(reinterpret_cast<uintptr_t>(g.out) & 15); C.cap = g.cap;
+            if (kMirror) C.hdst = a.host_dst + a.dst_off[blk];
             C.op = 0; C.flushed = 0; C.ring_lo = 0;
             pub = 0;
             gbase = g.payload - (reinterpret_cast<uintptr_t>(g.payload) & 15);
@@ -304,9 +311,10 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
             if (lane == 0) mbar_arrive(&q->empty[b]);
             const uint32_t lit_src = __shfl_sync(kFull, d.x, 0), lit = __shfl_sync(kFull, d.y, 0);
             const uint32_t mlen = __shfl_sync(kFull, d.z, 0), dist = __shfl_sync(kFull, d.w, 0);
-            C.flush(C.op, true);
+            C.template flush<kMirror>(C.op, true);
             __syncwarp();
             BCHK(a, C.op >= 0 && (long long)C.op + lit + mlen <= (long long)C.cap);
+            const int bulk_start = C.op;
             if (lit) warp_copy_ro(dst + C.op, gbase + lit_src, lit);
             int op = C.op + (int)lit;
             __syncwarp();
@@ -344,6 +352,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
             }
             op += (int)mlen;
             __syncwarp();
+            if (kMirror) { warp_copy_rw(C.hdst + bulk_start, dst + bulk_start, (uint32_t)(op - bulk_start)); __syncwarp(); }
             C.op = op; C.flushed = op;
             C.preload(op);
             __syncwarp();
@@ -357,7 +366,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
             const int op1 = __shfl_sync(kFull, lit_dst + (int)(lit + mlen), cnt - 1);
             const int m_dst = lit_dst + (int)lit;
             const int from = m_dst - (int)dist;
-            C.flush(op0, false);                       // previous batches leave for global memory (128-bit stores)
+            C.template flush<kMirror>(op0, false);     // previous batches leave for global memory (128-bit stores)
             if (kPublish && C.flushed >= (pub + 1) * a.seg_bytes) publish(min(C.flushed / a.seg_bytes, a.n_segs - 1));
             BCHK(a, op0 >= 0 && op1 >= op0 && op1 <= C.cap);
             const int ring_base = max(C.ring_lo, op1 - kOutRing);       // output positions >= this are in the ring; below: in global memory
@@ -442,7 +451,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
         batch++;
 
         if (cf & kEndBlock) {
-            if (result >= 0 && dst) { C.flush(C.op, true); __syncwarp(); }
+            if (result >= 0 && dst) { C.template flush<kMirror>(C.op, true); __syncwarp(); }
             if (kPublish) publish(a.n_segs);           // the block is over (short, failed or complete): nothing more will come
             if (lane == 0) a.out_len[blk] = result;
             if (result > 0) { C.dict_end = dst + result; C.dict_len = (uint32_t)result; last_out = dst; last_len = result; }   // cbits/lz4.c:2353-2355
@@ -463,7 +472,7 @@ __device__ void copier_main(const DecompressArgs& a, DQueue* q, uint32_t in_s, u
 // Two register budgets: 16 CTAs per SM (64 registers, a few spilled bytes) when a launch has more than 12 streams per SM
 // to keep busy, 12 CTAs per SM (80 registers, no spills) when everything is resident anyway -- measured +6 % on config 2's
 // single wave, -12 % on 16 384 blocks of 64 KiB if used there.
-template <int kCtasPerSm, bool kPublish = false>
+template <int kCtasPerSm, bool kPublish = false, bool kMirror = false>
 __global__ void __launch_bounds__(64, kCtasPerSm)
 decompress_kernel(DecompressArgs a)
 {
@@ -479,7 +488,7 @@ decompress_kernel(DecompressArgs a)
     asm volatile("mov.u32 %0, %1;" : "=r"(in_s) : "r"(smem_u32(in_ring)));
     asm volatile("mov.u32 %0, %1;" : "=r"(out_s) : "r"(smem_u32(out_ring)));
     if (threadIdx.x < 32) parser_main(a, &queue, in_s);
-    else copier_main<kPublish>(a, &queue, in_s, out_s);
+    else copier_main<kPublish, kMirror>(a, &queue, in_s, out_s);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t done = atomicAdd(&a.scratch->work_counter[3], 1u);
@@ -515,6 +524,14 @@ cudaError_t launch_decompress(const DecompressArgs& a, cudaStream_t stream)
     // them that the narrow kernel would leave most of the GPU idle (measured: 128 streams 17 -> 35 GB/s on mixed data, 11 ->
     // 49 GB/s on text; with more than two streams per SM the narrow kernel's 16 CTAs per SM win).  Independent blocks gain
     // nothing from it -- a block has ONE token chain, so only one of the eight parsers would work.
+    if (a.host_dst) {                       // host call with a page-locked destination: the output goes home from inside the kernel
+        if (a.n_streams <= sm_count * 12) decompress_kernel<12, false, true><<<a.n_streams, 64, 0, stream>>>(b);
+        else {
+            const int max_ctas = sm_count * 16;
+            decompress_kernel<16, false, true><<<a.n_streams < max_ctas ? a.n_streams : max_ctas, 64, 0, stream>>>(b);
+        }
+        return cudaGetLastError();
+    }
     if (a.seg_count) {                      // streamed host call: independent blocks, output leaves segment by segment
         if (a.n_streams <= sm_count * 12) decompress_kernel<12, true><<<a.n_streams, 64, 0, stream>>>(b);
         else {

@@ -32,6 +32,9 @@ struct DecompressArgs {
     // streamed launch (NULL: off): every block of the launch has the same capacity, cut into n_segs segments of seg_bytes;
     // seg_count[s] counts the blocks whose segment s is in global memory, the last one sets host_ready[s] (mapped host memory)
     uint32_t* seg_count; uint32_t* host_ready; int seg_bytes; int n_segs;
+    // mirrored launch (NULL: off; independent blocks only): block i's output is ALSO stored at host_dst + dst_off[i], page-locked
+    // host memory with host_dst congruent to dst modulo 16
+    uint8_t* host_dst;
 };
 
 // decompress_kernel_wide keeps its parsed-ahead sequence descriptors in global memory (L2): per CTA, kWideParsers rings of

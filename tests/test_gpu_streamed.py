@@ -1,7 +1,8 @@
 """Streamed host call (csrc/api.cu: compress_host_streamed; compress.cu: kStreamed): a batch of equally long independent
 blocks at a constant pitch is sent to the device segment by segment in deadline order, and the finders run while their
 blocks are still arriving.  The bytes must be the reference's whatever the order of arrival: every schedule extreme
-(plain block order, segment-major, the tuned default), host pitches with gaps, a short last block, and the SAME device
+(plain block order, segment-major, the tuned default), each way of raising the arrival flags and of sending the decoded
+output home, host pitches with gaps, a short last block, and the SAME device
 addresses reused by consecutive calls with different data (a 32-byte L1 sector read before it has landed would show up
 as the previous call's bytes)."""
 import os
@@ -84,8 +85,10 @@ print("streamed ok")
 
 @pytest.mark.parametrize("env", [{}, {"B200LZ4_STREAM_W": "0"}, {"B200LZ4_STREAM_W": "1000"},
                                  {"B200LZ4_STREAM_W": "0.7", "B200LZ4_STREAM_G": "5", "B200LZ4_STREAM_S": "13"},
+                                 {"B200LZ4_STREAM_FLAG": "copy", "B200LZ4_DECODE_OUT": "mirror"},
+                                 {"B200LZ4_STREAM_FLAG": "kernel", "B200LZ4_DECODE_OUT": "copy"},
                                  {"B200LZ4_NO_STREAMED": "1"}],
-                         ids=["tuned", "block-order", "segment-major", "odd-geometry", "plain-pipeline"])
+                         ids=["tuned", "block-order", "segment-major", "odd-geometry", "flag-copies+mirror", "flag-kernels+copy", "plain-pipeline"])
 def test_streamed_call_is_byte_identical(ctx, ref, env):
     e = dict(os.environ, B200LZ4_DEBUG="1", **env)
     out = subprocess.run([sys.executable, "-c", BODY % {"root": ROOT}], cwd=ROOT, env=e,

@@ -27,7 +27,7 @@ dst = ctx.pinned("d", int((lens.astype(np.int64) + lens // 255 + 24).sum()))
 
 
 def run(label, env):
-    for k in ("B200LZ4_STREAM_W", "B200LZ4_STREAM_G", "B200LZ4_STREAM_S", "B200LZ4_DEBUG", "B200LZ4_STREAM_COPY"):
+    for k in ("B200LZ4_STREAM_W", "B200LZ4_STREAM_G", "B200LZ4_STREAM_S", "B200LZ4_DEBUG", "B200LZ4_STREAM_FLAG", "B200LZ4_DECODE_OUT"):
         os.environ.pop(k, None)
     os.environ.update(env)
     if args.debug:
@@ -46,12 +46,12 @@ def run(label, env):
 
 
 if args.matrix:
-    for copy in ("2d", "batch"):
-        for S, W in ((8, None), (8, "0.75"), (8, "1.0"), (8, "1.25"), (4, None), (4, "0.5"), (4, "0.8"), (5, None), (6, None)):
-            env = {"B200LZ4_STREAM_COPY": copy, "B200LZ4_STREAM_S": str(S)}
-            if W:
-                env["B200LZ4_STREAM_W"] = W
-            run(f"copy={copy} S={S} W={W or 'auto'}", env)
+    run("auto", {})
+    for G, S, W in ((12, 4, None), (12, 8, None), (12, 4, "0.5"), (12, 4, "1.0"), (12, 4, "1.5")):
+        env = {"B200LZ4_STREAM_S": str(S), "B200LZ4_STREAM_G": str(G)}
+        if W:
+            env["B200LZ4_STREAM_W"] = W
+        run(f"G={G} S={S} W={W or 'auto'}", env)
 for w in ([] if args.matrix else args.sweep.split(",")):
     if w == "auto":
         run("auto", {})
@@ -66,19 +66,15 @@ run("auto again", {})
 rc, doff, ol = ctx.compress_batch(src[:total], offs, lens, args.accel, 8, dst)
 c_off = doff[:-1].copy(); c_len = (ol + 8).astype(np.int32)
 back = ctx.pinned("b", total + 64)
-dcases = [("decompress auto", {}), ("decompress G=16", {"B200LZ4_STREAM_G": "16"}), ("decompress G=8 S=16", {"B200LZ4_STREAM_G": "8", "B200LZ4_STREAM_S": "16"}),
-          ("decompress G=12 S=4", {"B200LZ4_STREAM_S": "4"})]
-if args.matrix:
-    dcases = [(f"decompress copy={cp} G={g} S={sg}", {"B200LZ4_STREAM_COPY": cp, "B200LZ4_STREAM_G": str(g), "B200LZ4_STREAM_S": str(sg)})
-              for cp in ("2d", "batch") for g, sg in ((12, 8), (12, 4), (16, 4), (16, 2), (8, 4))]
-    dcases.append(("decompress auto", {}))
+dcases = [("decompress mirror (default)", {}), ("decompress pieces", {"B200LZ4_DECODE_OUT": "pieces"}), ("decompress copy", {"B200LZ4_DECODE_OUT": "copy"}),
+          ("decompress mirror again", {})]
 for label, env in dcases:
-    for k in ("B200LZ4_STREAM_W", "B200LZ4_STREAM_G", "B200LZ4_STREAM_S", "B200LZ4_DEBUG", "B200LZ4_STREAM_COPY"):
+    for k in ("B200LZ4_STREAM_W", "B200LZ4_STREAM_G", "B200LZ4_STREAM_S", "B200LZ4_DEBUG", "B200LZ4_STREAM_FLAG", "B200LZ4_DECODE_OUT"):
         os.environ.pop(k, None)
     os.environ.update(env)
     best = 1e9
     for i in range(args.reps):
-        if i == args.reps - 1 and label == "decompress auto":
+        if i == args.reps - 1 and label == "decompress mirror (default)":
             os.environ["B200LZ4_DEBUG"] = "1"
         t = time.perf_counter()
         rc2, boff, blen = ctx.decompress_batch(dst, c_off, c_len, 8, 0, back)
