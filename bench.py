@@ -439,6 +439,7 @@ def run_gpu(args):
     e2e_launches = ctx.launch_count() - launches0          # counted by the library: chunks x (codec + scan + gather)
     assert rc == 0 and int(doff[-1]) == comp_total
     # the same call through the plain chunk pipeline (whole blocks land before their kernel starts), for comparison
+    prev_env = os.environ.get("B200LZ4_NO_STREAMED")
     os.environ["B200LZ4_NO_STREAMED"] = "1"
     ctx.compress_batch(src_view, offs, lens, ACCEL, HEADER, pin_dst)
     barrier()
@@ -447,7 +448,8 @@ def run_gpu(args):
         rc, doff, olen = ctx.compress_batch(src_view, offs, lens, ACCEL, HEADER, pin_dst)
     barrier()
     e2e_plain_wall = (time.perf_counter() - t_p0) / min(args.steps, 4)
-    del os.environ["B200LZ4_NO_STREAMED"]
+    if prev_env is None:
+        del os.environ["B200LZ4_NO_STREAMED"]
     assert rc == 0 and int(doff[-1]) == comp_total
     clocks = sampler.stop() if rank == 0 else None
     ceiling = copy_ceiling(ctx, pin_src, total, ctx.pinned("b_probe", comp_total), comp_total, 5, barrier)
