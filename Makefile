@@ -9,6 +9,7 @@ EXTRA  ?=
 NVFLAGS := $(EXTRA) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v -Iinclude -I$(CSRC)
 
 LIB    := $(PKG)/libb200lz4.so
+BOUNDS := $(PKG)/libb200lz4_bounds.so
 GEN    := $(PKG)/datagen/libb200gen.so
 HOSTT  := $(PKG)/csrc/host_mirror_test
 
@@ -28,7 +29,6 @@ oracle:
 	$(MAKE) -s -C oracle
 
 # debug build of the same library with destination-bounds checks in the decoder kernels (tests/test_gpu_modes.py)
-BOUNDS := $(PKG)/libb200lz4_bounds.so
 bounds: $(BOUNDS)
 $(BOUNDS): $(CU_SRCS) $(CU_HDRS)
 	$(NVCC) $(NVFLAGS) -DB200LZ4_BOUNDS_CHECK -shared -o $@ $(CU_SRCS) 2> /dev/null

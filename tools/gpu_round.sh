@@ -3,6 +3,7 @@
 # ncu launch list, ncu --set full of the four codec kernels (summarised on the box), per-kind probes, configs 3-5.
 # usage: tools/gpu_round.sh <tag>      (outputs under gpurun_out/; copy what should be judged into profiles/)
 # LIGHT=1: skip the ncu --set full captures and the kernel-resident probes (for visits that only changed the host pipeline)
+# MEDIUM=1: as LIGHT, but keep the ncu --set full captures of compress_kernel and decompress_kernel
 tag=${1:-r2}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_$tag.log
@@ -22,9 +23,13 @@ prof() {   # name, kernel regex, launches to skip, command...
   python tools/summarise_ncu.py gpurun_out/prof_${name}_$tag.ncu-rep gpurun_out/${tag}_${name}_ncu.txt --top 45 > /dev/null 2>&1
   rm -f gpurun_out/prof_${name}_$tag.ncu-rep
 }
+[ -n "$MEDIUM" ] && LIGHT=
 if [ -z "$LIGHT" ]; then
 prof compress_kernel 'compress_kernel$' 3 $SHORT
 prof decompress_kernel 'decompress_kernel' 3 $SHORT
+fi
+[ -n "$MEDIUM" ] && LIGHT=1
+if [ -z "$LIGHT" ]; then
 prof decompress_kernel_wide_text decompress_kernel_wide 1 python tools/linked_probe.py --streams 128 --mib-per-stream 4 --kinds text
 prof decompress_kernel_wide_mixed decompress_kernel_wide 1 python tools/linked_probe.py --streams 128 --mib-per-stream 4 --kinds mixed
 prof compress_kernel_wide_mixed compress_kernel_wide 1 python tools/linked_probe.py --streams 128 --mib-per-stream 4 --kinds mixed
