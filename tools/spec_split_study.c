@@ -196,6 +196,12 @@ int spec_split_study(const uint8_t* src, int32_t n, int accel, int32_t split, in
             }
         }
         if (in_run) { if (n - run_from > longest) longest = n - run_from; covered += n - run_from; }
+        /* sequences only the speculative parse has count as damage too */
+        if ((int64_t)(nsq - is) > after - missing) {
+            const int64_t extra = (int64_t)(nsq - is) - (after - missing);
+            if (missing == 0) { runs = 1; first_missing = S[is].start; }
+            missing += extra;
+        }
         r[1] = after; r[2] = missing; r[3] = runs; r[4] = longest; r[8] = first_missing; r[10] = covered;
     }
     free(T); free(S); free(pt); free(ps);
