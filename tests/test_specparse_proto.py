@@ -63,6 +63,10 @@ def test_linked_stream_is_byte_exact(built, lib, kind, accel):
     for warm_blocks in (1, 2, 3, 0):
         got, st = proto.compress_linked(lib, stream, [bs] * nb, accel, warm_blocks)
         assert got == want, f"{kind} accel {accel} warm {warm_blocks}: bytes differ from the oracle"
+        # the kernel plan's two claims: a worker's access log is implied by its sequences + catch-up lengths, and the block-level
+        # check run without a log (first access per bucket = minimum over access order) finds the same divergence as the log scan
+        assert st[17] == 0, "reconstructed access log differs from the logged one"
+        assert st[18] == nb - 1 and st[19] == 0, "log-free block check disagrees with the log scan"
 
 
 @pytest.mark.parametrize("seed", range(6))
@@ -83,5 +87,6 @@ def test_linked_stream_ragged_blocks(built, lib, seed):
     for accel in (1, 5):
         want = [o[8:] for o in ora.compress_chunks(arrays, accel, linked=True)]
         for warm_blocks in (1, 3):
-            got, _ = proto.compress_linked(lib, np.ascontiguousarray(stream), sizes, accel, warm_blocks)
+            got, st = proto.compress_linked(lib, np.ascontiguousarray(stream), sizes, accel, warm_blocks)
             assert got == want, f"seed {seed} kind {kind} accel {accel} warm {warm_blocks} sizes {sizes}"
+            assert st[17] == 0 and st[19] == 0

@@ -46,7 +46,7 @@
 #define EMPTY (-1)
 #define NSTATS 24
 
-typedef struct { int32_t start, anchor_before, end, dist; int32_t log_idx; int32_t floor_hit; } seq_t;
+typedef struct { int32_t start, anchor_before, end, dist; int32_t log_idx; int32_t floor_hit; int32_t catchup; } seq_t;
 typedef struct { int32_t pos, old; int32_t probe; } acc_t;
 
 static inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
@@ -98,11 +98,11 @@ static inline int probe(parser_t* P, int32_t pos, int32_t* cand)
     *cand = old;
     return 1;
 }
-static inline void push_seq(parser_t* P, int32_t start, int32_t anchor, int32_t end, int32_t dist, int floor_hit)
+static inline void push_seq(parser_t* P, int32_t start, int32_t anchor, int32_t end, int32_t dist, int floor_hit, int32_t catchup)
 {
     if (P->nseq == P->cap_seq) { P->cap_seq = P->cap_seq ? 2 * P->cap_seq : 1024; P->seqs = (seq_t*)realloc(P->seqs, sizeof(seq_t) * (size_t)P->cap_seq); }
     seq_t* s = &P->seqs[P->nseq++];
-    s->start = start; s->anchor_before = anchor; s->end = end; s->dist = dist; s->log_idx = P->nlog; s->floor_hit = floor_hit;
+    s->start = start; s->anchor_before = anchor; s->end = end; s->dist = dist; s->log_idx = P->nlog; s->floor_hit = floor_hit; s->catchup = catchup;
 }
 
 /* Runs the greedy parse of the current block from the saved state (a match end, or the block's beginning) until the
@@ -115,7 +115,7 @@ static int run(parser_t* P, int32_t stop_at)
     const int32_t last_probe = hi - MFLIMIT + 1, match_cap = hi - LAST_LITERALS;
     int32_t anchor = P->anchor, ip = anchor, cand = 0;
     const int32_t entered_at = anchor;
-    int floor_hit = 0;
+    int floor_hit = 0; int32_t catchup = 0;
     if (!P->started) {
         if (hi - P->begin < MIN_LENGTH) { P->ended_in_tail = 1; return 1; }     /* :921 */
         P->started = 1;
@@ -131,7 +131,7 @@ after_match:
         log_access(P, ip - 2, P->table[h2], 0);
         P->table[h2] = ip - 2;
     }
-    floor_hit = 0;
+    floor_hit = 0; catchup = 0;
     if (probe(P, ip, &cand)) goto match;                                        /* :1159-1196, no catch-up */
     ip++;                                                                        /* :1200 */
 search:
@@ -148,6 +148,7 @@ search:
         {   /* catch up, :1019: never below the block start for a candidate inside the block, never below the dictionary's start */
             const int32_t floor = cand >= P->blk_lo ? P->floor_blk : P->dict_lo;
             while (ip > anchor && cand > floor && src[ip - 1] == src[cand - 1]) { ip--; cand--; }
+            catchup = at - ip;
             /* the true parse's floor is the block start: a speculative catch-up that stopped AT its own origin may be short */
             floor_hit = (cand >= P->blk_lo && P->floor_blk > P->blk_lo && ip > anchor && cand == floor && src[ip - 1] == src[cand - 1]);
         }
@@ -159,7 +160,7 @@ match:
         int32_t k = 0;
         const int32_t cap = match_cap - (ip + 4);
         while (k < cap && src[ip + 4 + k] == src[cand + 4 + k]) k++;
-        push_seq(P, ip, anchor, ip + 4 + k, ip - cand, floor_hit);
+        push_seq(P, ip, anchor, ip + 4 + k, ip - cand, floor_hit, catchup);
         ip += 4 + k;
         anchor = ip;
         if (!P->snapped && anchor >= P->snap_from) {
@@ -190,6 +191,50 @@ static void parser_set_block(parser_t* P, int32_t lo, int32_t hi, int32_t prev_l
 }
 static void parser_free(parser_t* P) { if (P) { free(P->seqs); free(P->log); free(P); } }
 
+
+/* The access log of a whole-block parse is implied by its OUTPUT plus one number per sequence (the catch-up length, i.e.
+ * where the accepting probe stood): blind insert at the block's beginning, then per sequence the insert at (previous
+ * end - 2), the re-test at the previous end and, unless that one produced the sequence, the probes of the search run in
+ * closed form (cbits/lz4.c:957-969).  The VALUES read are not needed: the first access of a bucket after the sync point
+ * reads the snapshot's entry by definition.  Returns the number of positions where the reconstruction differs from the
+ * logged accesses (0 = the log need not be stored). */
+static int64_t reconstruct_and_compare(const parser_t* P)
+{
+    const int32_t last_probe = P->blk_hi - MFLIMIT + 1;
+    int64_t bad = 0; int L = 0;
+#define EXPECT(p, pr) do { if (L >= P->nlog || P->log[L].pos != (p) || P->log[L].probe != (pr)) bad++; L++; } while (0)
+    if (P->blk_hi - P->begin < MIN_LENGTH) return P->nlog ? 1 : 0;
+    EXPECT(P->begin, 0);
+    int32_t e = P->begin;               /* end of the previous sequence (the block's beginning before the first) */
+    for (int i = 0; i <= P->nseq; i++) {
+        const int have = i < P->nseq;
+        int from_retest = 0;
+        if (i > 0) {
+            if (e >= last_probe) break;                                  /* :1143: the tail begins, nothing more is touched */
+            EXPECT(e - 2, 0);
+            EXPECT(e, 1);
+            from_retest = have && P->seqs[i].start == e && P->seqs[i].anchor_before == e && P->seqs[i].catchup == 0;
+        }
+        if (!from_retest) {
+            const int32_t target = have ? P->seqs[i].start + P->seqs[i].catchup : INT32_MAX;
+            int32_t at = e + 1, step = 1, tick = P->accel << 6;
+            for (;;) {
+                const int32_t next = at + step;
+                step = tick++ >> 6;
+                if (next > last_probe) { if (have) bad++; break; }      /* the run ends in the tail */
+                EXPECT(at, 1);
+                if (at == target) break;
+                if (at > target) { bad++; break; }
+                at = next;
+            }
+        }
+        if (have) e = P->seqs[i].end;
+    }
+#undef EXPECT
+    if (L != P->nlog) bad++;
+    return bad;
+}
+
 /* ---- encoder of a sequence list (what emitter_main does on the device) ---- */
 static uint8_t* put_ext(uint8_t* op, uint32_t rest) { while (rest >= 255) { *op++ = 255; rest -= 255; } *op++ = (uint8_t)rest; return op; }
 static int encode(const uint8_t* src, int32_t hi, const seq_t* s, int ns, int32_t tail_from, uint8_t* dst)
@@ -218,12 +263,72 @@ static int encode(const uint8_t* src, int32_t hi, const seq_t* s, int ns, int32_
  * [7] log entries scanned by verifications and difference updates          [8] log entries replayed into tables
  * [9] sequences accepted from workers   [10] total sequences               [11] syncs that needed no serial step
  * [12] table accesses of all workers    [13] of the busiest worker         [14] of the serial part of phase 2
- * [15] of a plain serial parse (the baseline the critical path is compared with)     [16] verifications */
+ * [15] of a plain serial parse (the baseline the critical path is compared with)     [16] verifications
+ * [18] (linked) block-level checks also run in their log-free, kernel-shaped form   [19] of those, results that differ from the log scan's
+ * [17] (linked) positions where the access log RECONSTRUCTED from a worker's sequences + catch-up lengths differs from the logged one */
 
 static inline int bucket_differs(const parser_t* T, const int32_t* Stab, uint32_t b)
 {
     const int32_t a = T->table[b], c = Stab[b];
     return !(a == c || (!reachable(T, T->anchor, a) && !reachable(T, T->anchor, c)));
+}
+
+
+/* The block-level check in the shape a kernel would run it, without any log: every access position follows from the
+ * worker's sequences (+ catch-up lengths); "first access per bucket" is a minimum over access order (atomicMin on the
+ * device); a differing bucket whose first access is a probe that decides differently under the true value marks a
+ * divergence, the earliest one wins.  `Ttab` = true table, `snap` = the worker's table, both at the block's beginning.
+ * returns the order index of the earliest deciding-differently access, -1 if the whole block is exact. */
+static int verify_block_logfree(const parser_t* S, const parser_t* G, const int32_t* Ttab)
+{
+    const int32_t last_probe = S->blk_hi - MFLIMIT + 1;
+    int32_t* pos = (int32_t*)malloc(sizeof(int32_t) * (size_t)(S->nlog + 8));
+    uint8_t* isprobe = (uint8_t*)malloc((size_t)(S->nlog + 8));
+    int n = 0;
+    /* (1) access positions in order: embarrassingly parallel over sequences on the device, closed-form inside a run */
+    if (S->blk_hi - S->begin >= MIN_LENGTH) {
+        int32_t e = S->begin;
+        pos[n] = S->begin; isprobe[n++] = 0;
+        for (int i = 0; i <= S->nseq; i++) {
+            const int have = i < S->nseq;
+            int from_retest = 0;
+            if (i > 0) {
+                if (e >= last_probe) break;
+                pos[n] = e - 2; isprobe[n++] = 0;
+                pos[n] = e; isprobe[n++] = 1;
+                from_retest = have && S->seqs[i].start == e && S->seqs[i].anchor_before == e && S->seqs[i].catchup == 0;
+            }
+            if (!from_retest) {
+                const int32_t target = have ? S->seqs[i].start + S->seqs[i].catchup : INT32_MAX;
+                int32_t at = e + 1, step = 1, tick = S->accel << 6;
+                for (;;) {
+                    const int32_t next = at + step;
+                    step = tick++ >> 6;
+                    if (next > last_probe) break;
+                    pos[n] = at; isprobe[n++] = 1;
+                    if (at >= target) break;
+                    at = next;
+                }
+            }
+            if (have) e = S->seqs[i].end;
+        }
+    }
+    /* (2) first access per bucket (atomicMin of the order index) */
+    int32_t first[HASH_ENTRIES];
+    for (int b = 0; b < HASH_ENTRIES; b++) first[b] = INT32_MAX;
+    for (int i = 0; i < n; i++) { const uint32_t b = hash5(S->src + pos[i]); if (i < first[b]) first[b] = i; }
+    /* (3) every differing bucket, independently */
+    int bad = INT32_MAX;
+    for (uint32_t b = 0; b < HASH_ENTRIES; b++) {
+        const int32_t a = Ttab[b], c = S->snap[b];
+        if (a == c || (!reachable(G, G->blk_lo, a) && !reachable(G, G->blk_lo, c))) continue;
+        const int i = first[b];
+        if (i == INT32_MAX || !isprobe[i]) continue;
+        const int da = accepts(G, pos[i], a), dc = accepts(G, pos[i], c);
+        if ((da != dc || (da && a != c)) && i < bad) bad = i;
+    }
+    free(pos); free(isprobe);
+    return bad == INT32_MAX ? -1 : bad;
 }
 
 /* Phase 2 for one unit: the true parser T stands at a match end (or at the beginning of its block: T->started == 0)
@@ -291,6 +396,11 @@ static int merge_unit(parser_t* T, parser_t* S, int32_t to, int j0, int at_block
             }
         }
         stats[7] += L - L0;
+        if (first && S->logging) {           /* linked blocks: the kernel-shaped, log-free check must find the same divergence */
+            const int lf = verify_block_logfree(S, T, T->table);
+            stats[18]++;
+            if (lf != bad) stats[19]++;
+        }
         /* accept the worker's sequences completed before the divergence (all of them if there is none) */
         const int j_first = first ? 0 : j + 1;
         int j_last = j_first - 1;
@@ -301,7 +411,7 @@ static int merge_unit(parser_t* T, parser_t* S, int32_t to, int j0, int at_block
         }
         spec_applied = L0;
         if (j_last >= j_first) {
-            for (int q = j_first; q <= j_last; q++) push_seq(T, S->seqs[q].start, S->seqs[q].anchor_before, S->seqs[q].end, S->seqs[q].dist, 0);
+            for (int q = j_first; q <= j_last; q++) push_seq(T, S->seqs[q].start, S->seqs[q].anchor_before, S->seqs[q].end, S->seqs[q].dist, 0, S->seqs[q].catchup);
             stats[9] += j_last - j_first + 1;
             const int L1 = S->seqs[j_last].log_idx;
             for (int x = L0; x < L1; x++) T->table[hash5(src + S->log[x].pos)] = S->log[x].pos;      /* per-bucket max: parallel */
@@ -413,6 +523,7 @@ int specparse_compress_linked(const uint8_t* src, const int32_t* off, int nblock
         memcpy(P->snap, P->table, sizeof P->snap); P->snapped = 1; P->snap_log_idx = 0; P->snap_seq_idx = 0;
         P->logging = 1;
         run(P, off[k + 1] + 1);
+        stats[17] += reconstruct_and_compare(P);
         stats[1] += P->bytes_parsed; if (P->bytes_parsed > stats[2]) stats[2] = P->bytes_parsed;
         stats[12] += P->accesses; if (P->accesses > stats[13]) stats[13] = P->accesses;
     }

@@ -67,7 +67,7 @@ def main():
     ap.add_argument("--seg", default="262144,131072")
     ap.add_argument("--warm", default="65536,131072")
     ap.add_argument("--accels", default="1,400")
-    ap.add_argument("--kinds", default="text,mixed,records,sparse01,random,zero")
+    ap.add_argument("--kinds", default="text,mixed,records,sparse01,bits01,biased01,random,zero")
     ap.add_argument("--linked-streams", type=int, default=2)
     ap.add_argument("--linked-block", type=int, default=65536)
     ap.add_argument("--linked-blocks", type=int, default=64)
