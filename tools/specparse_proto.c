@@ -264,6 +264,7 @@ static int encode(const uint8_t* src, int32_t hi, const seq_t* s, int ns, int32_
  * [9] sequences accepted from workers   [10] total sequences               [11] syncs that needed no serial step
  * [12] table accesses of all workers    [13] of the busiest worker         [14] of the serial part of phase 2
  * [15] of a plain serial parse (the baseline the critical path is compared with)     [16] verifications
+ * [20] units (or rests of units) taken over by a 4096-wide merge of the worker's final table instead of a log replay
  * [18] (linked) block-level checks also run in their log-free, kernel-shaped form   [19] of those, results that differ from the log scan's
  * [17] (linked) positions where the access log RECONSTRUCTED from a worker's sequences + catch-up lengths differs from the logged one */
 
@@ -410,6 +411,20 @@ static int merge_unit(parser_t* T, parser_t* S, int32_t to, int j0, int at_block
             j_last = q;
         }
         spec_applied = L0;
+        if (bad < 0) {
+            /* everything the worker produced from this sync point on is exact: it ran to its first match end >= `to`, or into
+             * the block's tail.  No replay is needed then: every access after the sync point has a position >= (sync - 2)
+             * (the insert at :1146 is the lowest; everything before the sync point lies at least 4 bytes below it), so the
+             * worker's FINAL table tells which buckets it touched since, and with what: a 4096-wide merge. */
+            const int32_t threshold = first ? T->blk_lo : T->anchor - 2;
+            for (int q = j_first; q < S->nseq; q++) push_seq(T, S->seqs[q].start, S->seqs[q].anchor_before, S->seqs[q].end, S->seqs[q].dist, 0, S->seqs[q].catchup);
+            stats[9] += S->nseq - j_first;
+            for (int b = 0; b < HASH_ENTRIES; b++) if (S->table[b] != EMPTY && S->table[b] >= threshold) T->table[b] = S->table[b];
+            stats[20]++;
+            if (S->nseq > j_first) { T->anchor = S->seqs[S->nseq - 1].end; T->started = 1; }
+            if (S->ended_in_tail) { tail = 1; T->started = 1; T->ended_in_tail = 1; }
+            break;
+        }
         if (j_last >= j_first) {
             for (int q = j_first; q <= j_last; q++) push_seq(T, S->seqs[q].start, S->seqs[q].anchor_before, S->seqs[q].end, S->seqs[q].dist, 0, S->seqs[q].catchup);
             stats[9] += j_last - j_first + 1;
@@ -421,14 +436,6 @@ static int merge_unit(parser_t* T, parser_t* S, int32_t to, int j0, int at_block
             spec_applied = L1;
             j = j_last;
             first = 0;
-        }
-        if (bad < 0) {
-            /* everything the worker produced is exact: it ran to its first match end >= `to`, or into the block's tail.  The
-             * accesses after its last sequence (probes that found nothing) belong to the true parse as well. */
-            for (int x = spec_applied; x < S->nlog; x++) T->table[hash5(src + S->log[x].pos)] = S->log[x].pos;
-            stats[8] += S->nlog - spec_applied;
-            if (S->ended_in_tail) { tail = 1; T->started = 1; T->ended_in_tail = 1; }
-            break;
         }
         stats[6]++;
         tail = run(T, T->anchor + 1);       /* repair: the true parse takes the diverging step itself */

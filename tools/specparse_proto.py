@@ -53,7 +53,7 @@ def compress_linked(lib, stream: np.ndarray, sizes, accel: int, warm_blocks: int
 def row(kind, accel, a, b, exact, k, tot):
     # critical path in table accesses (one access = one step of the finder's serial chain): the busiest worker, then the serial
     # part of phase 2; its data-parallel parts (log scans, replays, 4096-bucket compares) at 1/32 (one warp) each
-    crit = tot[13] / k + tot[14] / k + (tot[7] + tot[8]) / k / 32 + tot[5] / k * 4096 / 32
+    crit = tot[13] / k + tot[14] / k + (tot[7] + tot[8]) / k / 32 + (tot[5] + tot[20]) / k * 4096 / 32
     return (f"{kind:9s} {accel:5d} {a:7d} {b:7d} | {exact:>5s} | {tot[0] // k:7d} {tot[12] / max(1, tot[15]):6.2f} {tot[13] // k:14d} | {tot[3] // k:12d} {tot[14] // k:10d} {tot[6] // k:7d} "
             f"{tot[7] // k:11d} {tot[8] // k:12d} | {tot[15] // k:9d} {crit:9.0f} {tot[15] / k / crit:8.1f}")
 
@@ -116,7 +116,8 @@ def main():
                     print(row(kind, accel, bs, wb, f"{exact}/{k}", k, tot))
     print("per block: work x = table accesses of all workers / accesses of the plain serial parse (warm-ups are the overhead); busiest worker = its accesses;")
     print("serial bytes / acc = what the in-order phase had to parse itself (sync steps, repairs); diverg. = verifications that found a deciding difference;")
-    print("crit path = busiest worker + serial acc + (log entries scanned + replayed + 4096 per verification) / 32, in table accesses (= steps of a finder's chain);")
+    print("crit path = busiest worker + serial acc + (log entries scanned + replayed + 4096 per full table compare and per final-table merge) / 32, in table accesses")
+    print("(= steps of a finder's chain); log replayed counts only partial take-overs (up to a divergence): a unit that verifies to its end is merged from the worker's final table;")
     print("speed-up = accesses of the plain serial parse / crit path (match-length counting is not in this unit: it is warp-parallel already)")
 
 
