@@ -31,6 +31,11 @@
  *
  * Soundness: by induction over worker k's accesses after sync -- an access reads either a value written after sync by an
  * access already shown equal in both parses, or the pre-sync value, which is the first-access case that was checked.
+ * What a kernel would NOT need (checked here on every linked test stream, stats [17]-[20]): the access log -- it follows
+ * from a worker's sequences plus one number per sequence, the catch-up length (reconstruct_and_compare), and the values
+ * read at first accesses are the snapshot's entries; the sequential log scan -- first access per bucket is a minimum over
+ * access order and every differing bucket is judged independently (verify_block_logfree); the log replay -- a unit that
+ * verifies to its end is taken over by a 4096-wide merge of the worker's final table.
  * The statistics returned say how much was left to the serial part.  Driven by tools/specparse_proto.py and
  * tests/test_specparse_proto.py (bytes compared with the oracle's).
  */
