@@ -96,5 +96,11 @@ def test_streamed_call_is_byte_identical(ctx, ref, env):
     assert out.returncode == 0, out.stdout[-4000:]
     assert "streamed ok" in out.stdout
     took_streamed_path = "[b200lz4] streamed:" in out.stdout
+    if "B200LZ4_NO_STREAMED" not in env and not took_streamed_path:
+        import re
+        m = re.search(r"hardware queues: (\d+) of", out.stdout)
+        if m and int(m.group(1)) < 2:       # measured by the library at ctx creation (api.cu: probe_stream_aliasing)
+            pytest.skip("this platform gave the library fewer than two kernel queues independent of the copy queues: "
+                        "streamed calls are off by design; the bytes above were verified through the plain pipeline")
     assert took_streamed_path == ("B200LZ4_NO_STREAMED" not in env), out.stdout[-2000:]
     assert "gave up" not in out.stdout, "finders timed out waiting for their input: the call fell back to the plain pipeline"
